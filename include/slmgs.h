@@ -1,0 +1,154 @@
+/* slmgs.h -- C ABI of libslmgs.so: the B200-native GS / WGS hologram loop.
+ *
+ * This is the drop-in boundary for ONE hot path of slmsuite (v0.4.1 @ 39243f08):
+ * `Hologram.optimize` / `SpotHologram.optimize` -> `optimize_gs`
+ * (slmsuite/holography/algorithms/_hologram.py:1351-1368, :1427-1493).  slmsuite has no FFI
+ * of its own: its only backend seam is the module alias `cp` (algorithms/_header.py:16-32)
+ * and subclass overrides of `_nearfield2farfield` / `_gs_farfield_routines` /
+ * `_farfield2nearfield` / `_update_weights`.  Each entry point below cites the reference
+ * method it replaces; INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all host buffers are C-contiguous and borrowed for the
+ *     duration of the call (nothing is retained);
+ *   - images are exchanged in the REFERENCE's centred (fftshift-ed) convention, shape
+ *     [batch][H][W]; SLM-sized arrays are [batch][h][w]; the library stores them rolled;
+ *   - every function returns 0 on success or a negative slmgs_status; the message is
+ *     available from slmgs_last_error(ctx);
+ *   - a context is bound to one device and one stream and is NOT thread-safe; different
+ *     contexts may be driven from different threads;
+ *   - compute entry points are asynchronous on the context's stream; getters synchronise.
+ */
+#ifndef SLMGS_H
+#define SLMGS_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SLMGS_API __attribute__((visibility("default")))
+#else
+#define SLMGS_API
+#endif
+
+typedef struct slmgs_ctx slmgs_ctx;
+
+typedef enum {
+    SLMGS_OK = 0,
+    SLMGS_ERR_INVALID = -1, /* bad argument / unsupported shape */
+    SLMGS_ERR_CUDA = -2,    /* CUDA runtime error */
+    SLMGS_ERR_OOM = -3,     /* allocation failed */
+    SLMGS_ERR_STATE = -4    /* call sequence error (e.g. constrain without forward) */
+} slmgs_status;
+
+/* ALGORITHM_DEFAULTS keys, algorithms/_header.py:53-71 */
+typedef enum {
+    SLMGS_GS = 0,
+    SLMGS_WGS_LEONARDO = 1,
+    SLMGS_WGS_KIM = 2,
+    SLMGS_WGS_NOGRETTE = 3,
+    SLMGS_WGS_WU = 4,
+    SLMGS_WGS_TANH = 5
+} slmgs_method;
+
+/* how the far-field phase is obtained in the constraint, _hologram.py:1556-1605 */
+typedef enum {
+    SLMGS_PHASE_COMPUTE = 0,       /* phase_ff = angle(farfield), not kept */
+    SLMGS_PHASE_COMPUTE_STORE = 1, /* phase_ff = angle(farfield), kept (WGS-Kim: iteration that fixes) */
+    SLMGS_PHASE_STORED = 2         /* use the stored phase_ff (fixed_phase) */
+} slmgs_phase_mode;
+
+/* flags of one iteration (subset of Hologram.flags that the device needs) */
+typedef struct {
+    int method;             /* slmgs_method */
+    int update_weights;     /* "WGS" in method and iter > 0, _hologram.py:1552 */
+    int phase_mode;         /* slmgs_phase_mode */
+    float feedback_exponent; /* flags["feedback_exponent"] */
+    float feedback_factor;   /* flags["feedback_factor"] */
+    int mraf;               /* target has NaN noise region, _hologram.py:1495-1548 */
+    int mraf_has_factor;    /* flags["mraf_factor"] is not None */
+    float mraf_factor;
+} slmgs_params;
+
+SLMGS_API int slmgs_version(void);
+/* message of the last failure on ctx (ctx == NULL: last failure of slmgs_create) */
+SLMGS_API const char* slmgs_last_error(const slmgs_ctx* ctx);
+
+/* Hologram.__init__ state, _hologram.py:196-478.  shape = (H, W) powers of two in [16, 8192];
+ * slm_shape = (h, w) <= shape, any parity; batch >= 1 independent holograms. */
+SLMGS_API int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W, int h, int w);
+SLMGS_API int slmgs_destroy(slmgs_ctx* ctx);
+SLMGS_API int slmgs_sync(slmgs_ctx* ctx);
+/* device pointer of the [batch][h][w] float32 phase buffer (for an NCCL all-gather of final phases) */
+SLMGS_API void* slmgs_phase_device_ptr(slmgs_ctx* ctx);
+SLMGS_API void* slmgs_stream(slmgs_ctx* ctx);
+
+/* ---- state upload / download ------------------------------------------------------------ */
+SLMGS_API int slmgs_set_phase(slmgs_ctx*, const float* phase);            /* reset_phase, :570-601; [B][h][w] */
+SLMGS_API int slmgs_get_phase(slmgs_ctx*, float* phase);                  /* raw phase (get_phase adds pi on the host, :786-811) */
+SLMGS_API int slmgs_set_amp_scalar(slmgs_ctx*, float amp);                /* amp=None -> 1/sqrt(h w), :401-402 */
+SLMGS_API int slmgs_set_amp_array(slmgs_ctx*, const float* amp, int per_hologram); /* [h][w] or [B][h][w], already L2-normalised, :404-405 */
+SLMGS_API int slmgs_set_propagation(slmgs_ctx*, const float* kernel);     /* [h][w] or NULL, :408-415 */
+SLMGS_API int slmgs_set_target(slmgs_ctx*, const float* target, int shared); /* normalised target, NaN = MRAF noise, :760-766; [B][H][W] or [H][W] */
+SLMGS_API int slmgs_get_target(slmgs_ctx*, float* target);
+SLMGS_API int slmgs_reset_weights(slmgs_ctx*);                            /* weights = nan_to_num(target, nan=0), :603-614 */
+SLMGS_API int slmgs_set_weights(slmgs_ctx*, const float* weights);        /* set_weights, :820-840 */
+SLMGS_API int slmgs_get_weights(slmgs_ctx*, float* weights);
+SLMGS_API int slmgs_set_phase_ff(slmgs_ctx*, const float* phase_ff);
+SLMGS_API int slmgs_get_phase_ff(slmgs_ctx*, float* phase_ff);
+SLMGS_API int slmgs_get_amp_ff(slmgs_ctx*, float* amp_ff);
+SLMGS_API int slmgs_get_farfield(slmgs_ctx*, float* farfield_c64);        /* interleaved re/im, ortho-scaled */
+SLMGS_API int slmgs_get_nearfield(slmgs_ctx*, float* nearfield_c64);      /* [B][h][w] crop of ifft2 result (ROW_LAST), interleaved */
+
+/* ---- fused loop -------------------------------------------------------------------------- */
+/* optimize_gs with callback=None and no per-iteration statistics (:1465-1493):
+ * n_iter iterations, then _populate_results (:934-949).  params[i] are the flags of iteration i
+ * (the host runs the WGS-Kim state machine of :1556-1585, which only depends on the iteration
+ * count in this mode).  Supports GS, WGS-Leonardo/Kim/Wu/tanh with pixel ("computational")
+ * feedback and MRAF with GS; everything else goes through the stepped entry points. */
+SLMGS_API int slmgs_run(slmgs_ctx*, const slmgs_params* params, int n_iter, int populate);
+
+/* ---- stepped loop (callbacks, statistics, Nogrette, spot feedback, MRAF + WGS) ------------- */
+SLMGS_API int slmgs_forward(slmgs_ctx*);                                   /* _nearfield2farfield + _midloop_cleaning, :1038-1056, :951-959 */
+SLMGS_API int slmgs_update_weights(slmgs_ctx*, const slmgs_params*);       /* Hologram._update_weights, pixel feedback, :1914-1922 -> :1822-1879 */
+SLMGS_API int slmgs_set_spots(slmgs_ctx*, int n, const int* x, const int* y, const float* spot_amp); /* spot_knm_rounded, spot_amp, _spots.py:1490-1546 */
+SLMGS_API int slmgs_update_weights_spot(slmgs_ctx*, const slmgs_params*, int width); /* SpotHologram._update_weights, _spots.py:1573-1624 */
+SLMGS_API int slmgs_constrain_inverse(slmgs_ctx*, const slmgs_params*);    /* _gs_farfield_routines (constraint part) + _farfield2nearfield, :1587-1653, :1058-1073 */
+SLMGS_API int slmgs_populate(slmgs_ctx*);                                  /* _populate_results, :934-949 */
+
+/* ---- statistics ---------------------------------------------------------------------------- */
+/* _calculate_stats(amp_ff, target) pieces, _stats.py:7-116.  out[b][8] =
+ * {sum f^2, nansum t^2, nansum t f, ratio min, ratio max, err min, err max, err sum} and
+ * out2[b][2] = {err sum of squares, masked count}.  The host finishes the formulas. */
+SLMGS_API int slmgs_stats_pixel(slmgs_ctx*, double* out8, double* out2);
+/* analysis.take(amp_ff^2, centres, width, centered, integrate), analysis/__init__.py:61-204:
+ * out[b][n] float64 window powers; also total[b] = sum(amp_ff^2) */
+SLMGS_API int slmgs_window_power(slmgs_ctx*, int n, const int* x, const int* y, int width, double* out, double* total);
+
+/* device-side snapshot / restore of the near-field phase (re-run from the same start without H2D) */
+SLMGS_API int slmgs_save_phase(slmgs_ctx*);
+SLMGS_API int slmgs_restore_phase(slmgs_ctx*);
+
+/* ---- timing (CUDA events on the context's stream; torch.cuda.Event cannot see this stream) --- */
+SLMGS_API int slmgs_timer_start(slmgs_ctx*);
+SLMGS_API int slmgs_timer_stop(slmgs_ctx*, float* ms); /* synchronises */
+/* per-kernel profile: when enabled, every FFT kernel launch of slmgs_run / stepped calls is bracketed by
+ * events.  slmgs_profile_read synchronises and returns, for class k (0 row first, 1 row fused, 2 row last,
+ * 3 column forward, 4 column fused, 5 column inverse): ms[k] = summed duration, count[k] = launches; resets. */
+SLMGS_API int slmgs_profile_enable(slmgs_ctx*, int on);
+SLMGS_API int slmgs_profile_read(slmgs_ctx*, float* ms6, int* count6);
+
+/* ---- introspection (tests / bench) ---------------------------------------------------------- */
+/* number of kernels this context has launched since creation */
+SLMGS_API long long slmgs_launch_count(const slmgs_ctx*);
+/* launch geometry chosen for the two fused kernels: out[0..3] = row threads, row grid x, col threads, col grid x */
+SLMGS_API int slmgs_launch_geometry(const slmgs_ctx*, int* out4);
+/* time n back-to-back launches of one kernel with CUDA events on the context's stream.
+ * which: 0 = row fused, 1 = column fused (GS), 2 = row first, 3 = column forward (populate). ms_out = average ms per launch */
+SLMGS_API int slmgs_time_kernel(slmgs_ctx*, int which, int n, float* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLMGS_H */

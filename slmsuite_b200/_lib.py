@@ -1,0 +1,162 @@
+"""
+ctypes binding of ``libslmgs.so`` (C ABI declared in ``include/slmgs.h``).
+
+The product path has exactly one backend: the CUDA library built for sm_100a by
+``slmsuite_b200/csrc/Makefile`` (or ``__graft_entry__.build()``).  If it is missing or cannot
+be loaded, importing a hologram class works but creating one raises ``RuntimeError`` -- there is
+no CPU fallback.  ``use_library(path)`` exists so the CPU test-suite can point the same
+bindings at the host *emulation* of the kernel sources (``tests/_emu``, test infrastructure);
+nothing in the package calls it.
+"""
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIBRARY = os.path.join(_HERE, "libslmgs.so")
+
+_lib = None
+_lib_path = None
+
+# slmgs_status, include/slmgs.h
+OK, ERR_INVALID, ERR_CUDA, ERR_OOM, ERR_STATE = 0, -1, -2, -3, -4
+
+# slmgs_method: ALGORITHM_DEFAULTS keys of the reference (algorithms/_header.py:53-71)
+METHODS = {"GS": 0, "WGS-Leonardo": 1, "WGS-Kim": 2, "WGS-Nogrette": 3, "WGS-Wu": 4, "WGS-tanh": 5}
+PHASE_COMPUTE, PHASE_COMPUTE_STORE, PHASE_STORED = 0, 1, 2
+
+
+class Params(C.Structure):
+    """slmgs_params, include/slmgs.h."""
+
+    _fields_ = [
+        ("method", C.c_int),
+        ("update_weights", C.c_int),
+        ("phase_mode", C.c_int),
+        ("feedback_exponent", C.c_float),
+        ("feedback_factor", C.c_float),
+        ("mraf", C.c_int),
+        ("mraf_has_factor", C.c_int),
+        ("mraf_factor", C.c_float),
+    ]
+
+
+_fp = C.POINTER(C.c_float)
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_ctx = C.c_void_p
+_pp = C.POINTER(Params)
+
+# name -> (restype, argtypes); every symbol include/slmgs.h declares
+SIGNATURES = {
+    "slmgs_version": (C.c_int, []),
+    "slmgs_last_error": (C.c_char_p, [_ctx]),
+    "slmgs_create": (C.c_int, [C.POINTER(_ctx), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "slmgs_destroy": (C.c_int, [_ctx]),
+    "slmgs_sync": (C.c_int, [_ctx]),
+    "slmgs_phase_device_ptr": (C.c_void_p, [_ctx]),
+    "slmgs_stream": (C.c_void_p, [_ctx]),
+    "slmgs_set_phase": (C.c_int, [_ctx, _fp]),
+    "slmgs_get_phase": (C.c_int, [_ctx, _fp]),
+    "slmgs_set_amp_scalar": (C.c_int, [_ctx, C.c_float]),
+    "slmgs_set_amp_array": (C.c_int, [_ctx, _fp, C.c_int]),
+    "slmgs_set_propagation": (C.c_int, [_ctx, _fp]),
+    "slmgs_set_target": (C.c_int, [_ctx, _fp, C.c_int]),
+    "slmgs_get_target": (C.c_int, [_ctx, _fp]),
+    "slmgs_reset_weights": (C.c_int, [_ctx]),
+    "slmgs_set_weights": (C.c_int, [_ctx, _fp]),
+    "slmgs_get_weights": (C.c_int, [_ctx, _fp]),
+    "slmgs_set_phase_ff": (C.c_int, [_ctx, _fp]),
+    "slmgs_get_phase_ff": (C.c_int, [_ctx, _fp]),
+    "slmgs_get_amp_ff": (C.c_int, [_ctx, _fp]),
+    "slmgs_get_farfield": (C.c_int, [_ctx, _fp]),
+    "slmgs_get_nearfield": (C.c_int, [_ctx, _fp]),
+    "slmgs_run": (C.c_int, [_ctx, _pp, C.c_int, C.c_int]),
+    "slmgs_forward": (C.c_int, [_ctx]),
+    "slmgs_update_weights": (C.c_int, [_ctx, _pp]),
+    "slmgs_set_spots": (C.c_int, [_ctx, C.c_int, _ip, _ip, _fp]),
+    "slmgs_update_weights_spot": (C.c_int, [_ctx, _pp, C.c_int]),
+    "slmgs_constrain_inverse": (C.c_int, [_ctx, _pp]),
+    "slmgs_populate": (C.c_int, [_ctx]),
+    "slmgs_stats_pixel": (C.c_int, [_ctx, _dp, _dp]),
+    "slmgs_window_power": (C.c_int, [_ctx, C.c_int, _ip, _ip, C.c_int, _dp, _dp]),
+    "slmgs_save_phase": (C.c_int, [_ctx]),
+    "slmgs_restore_phase": (C.c_int, [_ctx]),
+    "slmgs_timer_start": (C.c_int, [_ctx]),
+    "slmgs_timer_stop": (C.c_int, [_ctx, _fp]),
+    "slmgs_profile_enable": (C.c_int, [_ctx, C.c_int]),
+    "slmgs_profile_read": (C.c_int, [_ctx, _fp, _ip]),
+    "slmgs_launch_count": (C.c_longlong, [_ctx]),
+    "slmgs_launch_geometry": (C.c_int, [_ctx, _ip]),
+    "slmgs_time_kernel": (C.c_int, [_ctx, C.c_int, C.c_int, _fp]),
+}
+
+
+def _bind(lib):
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def use_library(path):
+    """Load a specific build of the C ABI (tests use this for the host emulation)."""
+    global _lib, _lib_path
+    _lib = _bind(C.CDLL(path))
+    _lib_path = path
+    return _lib
+
+
+def library_path():
+    return _lib_path
+
+
+def lib():
+    """The loaded C ABI; loads ``libslmgs.so`` next to this file on first use."""
+    if _lib is None:
+        if not os.path.exists(DEFAULT_LIBRARY):
+            raise RuntimeError(
+                "slmsuite_b200: CUDA library not built ({} missing). Run `python -c 'import __graft_entry__ as g; "
+                "g.build()'` or `make -C slmsuite_b200/csrc`. There is no CPU fallback.".format(DEFAULT_LIBRARY)
+            )
+        try:
+            use_library(DEFAULT_LIBRARY)
+        except OSError as exc:
+            raise RuntimeError("slmsuite_b200: cannot load {}: {}".format(DEFAULT_LIBRARY, exc)) from exc
+    return _lib
+
+
+class SlmgsError(RuntimeError):
+    pass
+
+
+def check(ctx, status):
+    """Map slmgs_status to the exception types the reference raises."""
+    if status == OK:
+        return
+    msg = lib().slmgs_last_error(ctx)
+    msg = msg.decode() if msg else "slmgs error {}".format(status)
+    if status == ERR_INVALID:
+        raise ValueError(msg)
+    if status == ERR_OOM:
+        raise MemoryError(msg)
+    raise SlmgsError(msg)
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def fptr(a):
+    return a.ctypes.data_as(_fp)
+
+
+def dptr(a):
+    return a.ctypes.data_as(_dp)
+
+
+def iptr(a):
+    return a.ctypes.data_as(_ip)

@@ -1,0 +1,1027 @@
+// slmgs_api.cu -- C ABI (include/slmgs.h): context, state upload/download, fused and stepped
+// GS / WGS loop.  Compiled by nvcc into libslmgs.so; compiled by g++ with -DSLMGS_EMULATE into
+// the host-emulation library used by the CPU test-suite (tests/_emu, test infrastructure).
+#include "../../include/slmgs.h"
+#include "slmgs_dispatch.h"
+#include "slmgs_pointwise.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+using namespace slmgs;
+
+// ------------------------------------------------------------------------------------------
+// runtime shim
+// ------------------------------------------------------------------------------------------
+#ifdef SLMGS_EMULATE
+static int rt_set_device(int) { return 0; }
+static int rt_malloc(void** p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : 2; }
+static int rt_free(void* p) { free(p); return 0; }
+static int rt_h2d(void* d, const void* h, size_t n, rt_stream) { memcpy(d, h, n); return 0; }
+static int rt_d2h(void* h, const void* d, size_t n, rt_stream) { memcpy(h, d, n); return 0; }
+static int rt_memset(void* d, int v, size_t n, rt_stream) { memset(d, v, n); return 0; }
+static int rt_sync(rt_stream) { return 0; }
+static int rt_stream_create(rt_stream* s) { *s = nullptr; return 0; }
+static int rt_stream_destroy(rt_stream) { return 0; }
+static const char* rt_errstr(int e) { return e == 2 ? "out of memory" : "emulation error"; }
+static bool rt_is_oom(int e) { return e == 2; }
+static int rt_sm_count() { return 4; }
+#else
+static int rt_set_device(int d) { return (int)cudaSetDevice(d); }
+static int rt_malloc(void** p, size_t n) { return (int)cudaMalloc(p, n ? n : 1); }
+static int rt_free(void* p) { return (int)cudaFree(p); }
+static int rt_h2d(void* d, const void* h, size_t n, rt_stream s) {
+    int e = (int)cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s);
+    if (e) return e;
+    return (int)cudaStreamSynchronize(s);  // host buffer is only borrowed for the call
+}
+static int rt_d2h(void* h, const void* d, size_t n, rt_stream s) {
+    int e = (int)cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s);
+    if (e) return e;
+    return (int)cudaStreamSynchronize(s);
+}
+static int rt_memset(void* d, int v, size_t n, rt_stream s) { return (int)cudaMemsetAsync(d, v, n, s); }
+static int rt_sync(rt_stream s) { return (int)cudaStreamSynchronize(s); }
+static int rt_stream_create(rt_stream* s) { return (int)cudaStreamCreateWithFlags(s, cudaStreamNonBlocking); }
+static int rt_stream_destroy(rt_stream s) { return (int)cudaStreamDestroy(s); }
+static const char* rt_errstr(int e) { return cudaGetErrorString((cudaError_t)e); }
+static bool rt_is_oom(int e) { return e == (int)cudaErrorMemoryAllocation; }
+static int rt_sm_count() {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+#endif
+
+// ------------------------------------------------------------------------------------------
+// per-size dispatch
+// ------------------------------------------------------------------------------------------
+#define SLMGS_FOR_SIZES(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192)
+
+static bool size_supported(int n) {
+#define X(N_) if (n == N_) return true;
+    SLMGS_FOR_SIZES(X)
+#undef X
+    return false;
+}
+static LaunchInfo size_info(int n) {
+#define X(N_) if (n == N_) return launch_info_##N_();
+    SLMGS_FOR_SIZES(X)
+#undef X
+    LaunchInfo z;
+    memset(&z, 0, sizeof z);
+    return z;
+}
+static int launch_row(int n, int mode, int gx, int gy, int nt, rt_stream s, const RowArgs& a) {
+#define X(N_) if (n == N_) return launch_row_##N_(mode, gx, gy, nt, s, a);
+    SLMGS_FOR_SIZES(X)
+#undef X
+    return -1;
+}
+static int launch_col(int n, int mode, int gx, int gy, int nt, rt_stream s, const ColArgs& a) {
+#define X(N_) if (n == N_) return launch_col_##N_(mode, gx, gy, nt, s, a);
+    SLMGS_FOR_SIZES(X)
+#undef X
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+enum { ACC_W0 = 0, ACC_W1 = 1, ACC_FNORM = 2, ACC_MEAN = 3, ACC_S0 = 4, ACC_S1 = 5, ACC_S2 = 6, ACC_TMP = 7, ACC_N = 8 };
+
+struct slmgs_ctx {
+    int device, B, H, W, h, w, i0, i2;
+    rt_stream stream;
+    std::string err;
+    long long launches;
+    int sms;
+    // launch geometry
+    LaunchInfo irow, icol;
+    int row_threads, row_gx, col_threads, col_gx;
+    // device state
+    cf* fld;
+    cf* farfield;     // lazily allocated
+    cf* nearfield;    // lazily allocated, [B][h][w]
+    cf* stage_c;      // staging buffer for complex downloads (lazily allocated, B*H*W)
+    float* stage_f;   // staging for rolled uploads/downloads (B*H*W floats)
+    float *phase, *amp, *prop, *target, *weights, *phase_ff, *amp_ff;
+    cf *twA_row, *twB_row, *twA_col, *twB_col;
+    double* acc;      // [B][ACC_N]
+    double* partial;  // stats partials
+    int* spot_x;
+    int* spot_y;
+    float* spot_amp;
+    double* spot_pw;
+    int n_spots;
+    // host-side state
+    float amp_scalar;
+    int amp_per_hologram;
+    int target_shared;
+    int w_pending;     // accumulator slot of a not-yet-applied weight normalisation, or -1
+    bool ff_valid;     // farfield / amp_ff hold the transform of the current phase (stepped mode)
+    double fnorm;      // ||nearfield||_2 == ||farfield||_2 (Parseval, ortho), from the amplitude
+    float* phase_saved;
+    // timing
+    bool profiling;
+#ifndef SLMGS_EMULATE
+    cudaEvent_t t0, t1;
+    std::vector<cudaEvent_t> ev_pool;   // pairs
+    std::vector<int> ev_class;
+    size_t ev_used;
+#endif
+};
+
+static std::string g_create_error;
+
+static int fail(slmgs_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+static int rt_check(slmgs_ctx* c, int e, const char* what) {
+    if (e == 0) return 0;
+    return fail(c, rt_is_oom(e) ? SLMGS_ERR_OOM : SLMGS_ERR_CUDA, std::string(what) + ": " + rt_errstr(e));
+}
+#define RT(c, call)                                   \
+    do {                                              \
+        int e__ = rt_check((c), (call), #call);       \
+        if (e__) return e__;                          \
+    } while (0)
+#define CHECK_CTX(c) \
+    if (!(c)) return SLMGS_ERR_INVALID; \
+    RT(c, rt_set_device((c)->device))
+
+template <class T> static int dev_alloc(slmgs_ctx* c, T** p, size_t count) {
+    void* q = nullptr;
+    int e = rt_malloc(&q, count * sizeof(T));
+    if (e) return rt_check(c, e, "device allocation");
+    *p = (T*)q;
+    return 0;
+}
+
+static void make_twiddles(int n, std::vector<cf>& a, std::vector<cf>& b) {
+    LaunchInfo li = size_info(n);
+    (void)li;
+    // radices: recover from the plan through the instantiated sizes (R0 = N / M1)
+    int r0, r1, r2;
+    switch (n) {
+        case 16: r0 = 16; r1 = 1; r2 = 1; break;
+        case 32: r0 = 16; r1 = 2; r2 = 1; break;
+        case 64: r0 = 16; r1 = 4; r2 = 1; break;
+        case 128: r0 = 16; r1 = 8; r2 = 1; break;
+        case 256: r0 = 16; r1 = 16; r2 = 1; break;
+        case 512: r0 = 16; r1 = 16; r2 = 2; break;
+        case 1024: r0 = 16; r1 = 16; r2 = 4; break;
+        case 2048: r0 = 16; r1 = 16; r2 = 8; break;
+        case 4096: r0 = 16; r1 = 16; r2 = 16; break;
+        default: r0 = 32; r1 = 16; r2 = 16; break;
+    }
+    const int m1 = r1 * r2;
+    a.resize(n);
+    b.resize(m1);
+    const double tau = 6.283185307179586476925286766559;
+    for (int k0 = 0; k0 < r0; ++k0)
+        for (int j = 0; j < m1; ++j) {
+            const double ang = -tau * (double)((long long)j * k0 % n) / (double)n;
+            a[k0 * m1 + j] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+    for (int k1 = 0; k1 < r1; ++k1)
+        for (int n2 = 0; n2 < r2; ++n2) {
+            const double ang = -tau * (double)((n2 * k1) % m1) / (double)m1;
+            b[k1 * r2 + n2] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+static void choose_geometry(slmgs_ctx* c) {
+    const int want = 2 * c->sms;  // at least two waves of blocks when the problem allows
+    // rows: lines per block L = threads / tpl
+    {
+        const LaunchInfo& li = c->irow;
+        int lo = li.tpl < 32 ? 32 : li.tpl;
+        int nt = li.maxt;
+        while (nt > lo) {
+            const int lines = nt / li.tpl;
+            const long long blocks = (long long)((c->h + lines - 1) / lines) * c->B;
+            if (blocks >= want) break;
+            nt >>= 1;
+        }
+        int o = env_int("SLMGS_ROW_THREADS", 0);
+        if (o >= lo && o <= li.maxt && (o & (o - 1)) == 0) nt = o;
+        c->row_threads = nt;
+        const int lines = nt / li.tpl;
+        c->row_gx = (c->h + lines - 1) / lines;
+    }
+    // columns: C = threads / tpl columns per block; keep >= 4 columns (one 32-byte sector per row)
+    {
+        const LaunchInfo& li = c->icol;
+        int lo = li.tpl * 4;
+        if (lo < 32) lo = 32;
+        if (lo > li.maxt) lo = li.maxt;
+        int nt = li.maxt;
+        while (nt / li.tpl > c->W) nt >>= 1;
+        while (nt > lo) {
+            const long long blocks = (long long)(c->W / (nt / li.tpl)) * c->B;
+            if (blocks >= want) break;
+            nt >>= 1;
+        }
+        int o = env_int("SLMGS_COL_THREADS", 0);
+        if (o >= li.tpl && o >= 32 && o <= li.maxt && (o & (o - 1)) == 0 && o / li.tpl <= c->W) nt = o;
+        c->col_threads = nt;
+        c->col_gx = c->W / (nt / li.tpl);
+    }
+}
+
+extern "C" int slmgs_version(void) { return 100; }
+
+extern "C" const char* slmgs_last_error(const slmgs_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W, int h, int w) {
+    if (!out) return fail(nullptr, SLMGS_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (batch < 1) return fail(nullptr, SLMGS_ERR_INVALID, "batch must be >= 1");
+    if (!size_supported(H) || !size_supported(W))
+        return fail(nullptr, SLMGS_ERR_INVALID, "shape must be powers of two in [16, 8192] per dimension");
+    if (h < 1 || w < 1 || h > H || w > W) return fail(nullptr, SLMGS_ERR_INVALID, "slm_shape must fit inside shape");
+    int e = rt_set_device(device);
+    if (e) return fail(nullptr, SLMGS_ERR_CUDA, std::string("cudaSetDevice: ") + rt_errstr(e));
+    slmgs_ctx* c = new slmgs_ctx();
+    c->device = device;
+    c->B = batch; c->H = H; c->W = W; c->h = h; c->w = w;
+    // toolbox.unpad, toolbox/__init__.py:1701-1709: floor of half the difference
+    c->i0 = (H - h) / 2;
+    c->i2 = (W - w) / 2;
+    c->launches = 0;
+    c->sms = rt_sm_count();
+    c->irow = size_info(W);
+    c->icol = size_info(H);
+    c->fld = nullptr; c->farfield = nullptr; c->nearfield = nullptr; c->stage_c = nullptr; c->stage_f = nullptr;
+    c->phase = c->amp = c->prop = c->target = c->weights = c->phase_ff = c->amp_ff = nullptr;
+    c->twA_row = c->twB_row = c->twA_col = c->twB_col = nullptr;
+    c->acc = nullptr; c->partial = nullptr;
+    c->spot_x = c->spot_y = nullptr; c->spot_amp = nullptr; c->spot_pw = nullptr; c->n_spots = 0;
+    c->amp_scalar = (float)(1.0 / sqrt((double)h * (double)w));
+    c->amp_per_hologram = 0;
+    c->target_shared = 0;
+    c->w_pending = -1;
+    c->ff_valid = false;
+    c->fnorm = 1.0;
+    c->stream = nullptr;
+    c->phase_saved = nullptr;
+    c->profiling = false;
+#ifndef SLMGS_EMULATE
+    c->t0 = c->t1 = nullptr;
+    c->ev_used = 0;
+#endif
+    choose_geometry(c);
+#define CR(call)                                                   \
+    do {                                                           \
+        int e__ = (call);                                          \
+        if (e__) {                                                 \
+            g_create_error = c->err;                               \
+            slmgs_destroy(c);                                      \
+            return e__;                                            \
+        }                                                          \
+    } while (0)
+    CR(rt_check(c, rt_stream_create(&c->stream), "stream create"));
+    const size_t P = (size_t)H * W, S = (size_t)h * w, Bz = (size_t)batch;
+    CR(dev_alloc(c, &c->fld, Bz * P));
+    CR(dev_alloc(c, &c->phase, Bz * S));
+    CR(dev_alloc(c, &c->target, Bz * P));
+    CR(dev_alloc(c, &c->weights, Bz * P));
+    CR(dev_alloc(c, &c->phase_ff, Bz * P));
+    CR(dev_alloc(c, &c->amp_ff, Bz * P));
+    CR(dev_alloc(c, &c->stage_f, Bz * P));
+    CR(dev_alloc(c, &c->acc, Bz * ACC_N));
+    CR(dev_alloc(c, &c->partial, Bz * 256 * 8));
+    CR(rt_check(c, rt_memset(c->fld, 0, Bz * P * sizeof(cf), c->stream), "memset"));
+    CR(rt_check(c, rt_memset(c->phase, 0, Bz * S * sizeof(float), c->stream), "memset"));
+    CR(rt_check(c, rt_memset(c->target, 0, Bz * P * sizeof(float), c->stream), "memset"));
+    CR(rt_check(c, rt_memset(c->weights, 0, Bz * P * sizeof(float), c->stream), "memset"));
+    CR(rt_check(c, rt_memset(c->phase_ff, 0, Bz * P * sizeof(float), c->stream), "memset"));
+    CR(rt_check(c, rt_memset(c->amp_ff, 0, Bz * P * sizeof(float), c->stream), "memset"));
+    CR(rt_check(c, rt_memset(c->acc, 0, Bz * ACC_N * sizeof(double), c->stream), "memset"));
+    {
+        std::vector<cf> a, b;
+        make_twiddles(W, a, b);
+        CR(dev_alloc(c, &c->twA_row, a.size()));
+        CR(dev_alloc(c, &c->twB_row, b.size()));
+        CR(rt_check(c, rt_h2d(c->twA_row, a.data(), a.size() * sizeof(cf), c->stream), "twiddle upload"));
+        CR(rt_check(c, rt_h2d(c->twB_row, b.data(), b.size() * sizeof(cf), c->stream), "twiddle upload"));
+        make_twiddles(H, a, b);
+        CR(dev_alloc(c, &c->twA_col, a.size()));
+        CR(dev_alloc(c, &c->twB_col, b.size()));
+        CR(rt_check(c, rt_h2d(c->twA_col, a.data(), a.size() * sizeof(cf), c->stream), "twiddle upload"));
+        CR(rt_check(c, rt_h2d(c->twB_col, b.data(), b.size() * sizeof(cf), c->stream), "twiddle upload"));
+    }
+    CR(rt_check(c, rt_sync(c->stream), "sync"));
+#undef CR
+    *out = c;
+    return SLMGS_OK;
+}
+
+extern "C" int slmgs_destroy(slmgs_ctx* c) {
+    if (!c) return SLMGS_OK;
+    rt_set_device(c->device);
+    if (c->stream) rt_sync(c->stream);
+    void* ptrs[] = {c->fld, c->farfield, c->nearfield, c->stage_c, c->stage_f, c->phase, c->amp, c->prop, c->target,
+                    c->weights, c->phase_ff, c->amp_ff, c->twA_row, c->twB_row, c->twA_col, c->twB_col, c->acc,
+                    c->partial, c->spot_x, c->spot_y, c->spot_amp, c->spot_pw, c->phase_saved};
+    for (void* p : ptrs)
+        if (p) rt_free(p);
+#ifndef SLMGS_EMULATE
+    if (c->t0) cudaEventDestroy(c->t0);
+    if (c->t1) cudaEventDestroy(c->t1);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+#endif
+    if (c->stream) rt_stream_destroy(c->stream);
+    delete c;
+    return SLMGS_OK;
+}
+
+extern "C" int slmgs_sync(slmgs_ctx* c) {
+    CHECK_CTX(c);
+    RT(c, rt_sync(c->stream));
+    return SLMGS_OK;
+}
+extern "C" void* slmgs_phase_device_ptr(slmgs_ctx* c) { return c ? (void*)c->phase : nullptr; }
+extern "C" void* slmgs_stream(slmgs_ctx* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" long long slmgs_launch_count(const slmgs_ctx* c) { return c ? c->launches : 0; }
+extern "C" int slmgs_launch_geometry(const slmgs_ctx* c, int* out4) {
+    if (!c || !out4) return SLMGS_ERR_INVALID;
+    out4[0] = c->row_threads; out4[1] = c->row_gx; out4[2] = c->col_threads; out4[3] = c->col_gx;
+    return SLMGS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// element-wise helpers
+// ------------------------------------------------------------------------------------------
+static ElemArgs elem_args(slmgs_ctx* c, const void* src, void* dst, long long n) {
+    ElemArgs a;
+    memset(&a, 0, sizeof a);
+    a.src = src; a.dst = dst; a.n = n;
+    a.src_bs = n; a.dst_bs = n; a.target_bs = c->target_shared ? 0 : n;
+    a.target = c->target;
+    a.acc = c->acc; a.acc_bs = ACC_N;
+    a.H = c->H; a.W = c->W;
+    a.fnorm_slot = -1; a.mean_slot = -1;
+    return a;
+}
+template <int OP> static int launch_elem(slmgs_ctx* c, const ElemArgs& a, int batch) {
+    long long blocks = (a.n + 255) / 256;
+    const long long cap = (long long)c->sms * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    c->launches++;
+    return rt_check(c, launch_kernel<ElemKernel<OP>>((int)blocks, batch, 256, 0, c->stream, a), "element-wise launch");
+}
+static int zero_slot(slmgs_ctx* c, int slot, int count = 1) {
+    // slots of all holograms: strided -> one small memset per hologram would be B launches; clear via 2-D memset
+#ifdef SLMGS_EMULATE
+    for (int b = 0; b < c->B; ++b) memset(c->acc + (size_t)b * ACC_N + slot, 0, sizeof(double) * count);
+    return 0;
+#else
+    return rt_check(c, (int)cudaMemset2DAsync(c->acc + slot, ACC_N * sizeof(double), 0, sizeof(double) * count, c->B,
+                                               c->stream), "accumulator clear");
+#endif
+}
+
+// upload a centred image -> rolled device image
+static int upload_rolled(slmgs_ctx* c, const float* host, float* dst, int batch) {
+    const long long P = (long long)c->H * c->W;
+    RT(c, rt_h2d(c->stage_f, host, (size_t)batch * P * sizeof(float), c->stream));
+    ElemArgs a = elem_args(c, c->stage_f, dst, P);
+    return launch_elem<EW_ROLL_F32>(c, a, batch);
+}
+static int download_rolled(slmgs_ctx* c, const float* src, float* host, int batch) {
+    const long long P = (long long)c->H * c->W;
+    ElemArgs a = elem_args(c, src, c->stage_f, P);
+    int e = launch_elem<EW_ROLL_F32>(c, a, batch);  // roll by N/2 is an involution for even N
+    if (e) return e;
+    RT(c, rt_d2h(host, c->stage_f, (size_t)batch * P * sizeof(float), c->stream));
+    return SLMGS_OK;
+}
+
+// resolve a pending weight normalisation (fused WGS leaves weights un-normalised by one scalar)
+static int resolve_weights(slmgs_ctx* c) {
+    if (c->w_pending < 0) return SLMGS_OK;
+    ElemArgs a = elem_args(c, nullptr, c->weights, (long long)c->H * c->W);
+    a.slot0 = c->w_pending;
+    int e = launch_elem<EW_SCALE>(c, a, c->B);
+    c->w_pending = -1;
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------
+// state upload / download
+// ------------------------------------------------------------------------------------------
+extern "C" int slmgs_set_phase(slmgs_ctx* c, const float* phase) {
+    CHECK_CTX(c);
+    if (!phase) return fail(c, SLMGS_ERR_INVALID, "phase is NULL");
+    RT(c, rt_h2d(c->phase, phase, (size_t)c->B * c->h * c->w * sizeof(float), c->stream));
+    c->ff_valid = false;
+    return SLMGS_OK;
+}
+extern "C" int slmgs_get_phase(slmgs_ctx* c, float* phase) {
+    CHECK_CTX(c);
+    if (!phase) return fail(c, SLMGS_ERR_INVALID, "phase is NULL");
+    RT(c, rt_d2h(phase, c->phase, (size_t)c->B * c->h * c->w * sizeof(float), c->stream));
+    return SLMGS_OK;
+}
+extern "C" int slmgs_set_amp_scalar(slmgs_ctx* c, float amp) {
+    CHECK_CTX(c);
+    if (c->amp) {
+        RT(c, rt_sync(c->stream));
+        rt_free(c->amp);
+        c->amp = nullptr;
+    }
+    c->amp_scalar = amp;
+    c->fnorm = (double)amp * sqrt((double)c->h * (double)c->w);
+    c->ff_valid = false;
+    return SLMGS_OK;
+}
+extern "C" int slmgs_set_amp_array(slmgs_ctx* c, const float* amp, int per_hologram) {
+    CHECK_CTX(c);
+    if (!amp) return fail(c, SLMGS_ERR_INVALID, "amp is NULL");
+    const size_t S = (size_t)c->h * c->w, n = per_hologram ? S * c->B : S;
+    if (c->amp) {
+        RT(c, rt_sync(c->stream));
+        rt_free(c->amp);
+        c->amp = nullptr;
+    }
+    int e = dev_alloc(c, &c->amp, n);
+    if (e) return e;
+    RT(c, rt_h2d(c->amp, amp, n * sizeof(float), c->stream));
+    c->amp_per_hologram = per_hologram ? 1 : 0;
+    // Parseval: ||farfield|| = ||nearfield|| = ||amp|| (first hologram's amp is representative: the
+    // constructor L2-normalises every amp, _hologram.py:404-405)
+    double s = 0.0;
+    for (size_t i = 0; i < S; ++i) s += (double)amp[i] * (double)amp[i];
+    c->fnorm = sqrt(s);
+    c->ff_valid = false;
+    return SLMGS_OK;
+}
+extern "C" int slmgs_set_propagation(slmgs_ctx* c, const float* kernel) {
+    CHECK_CTX(c);
+    if (c->prop) {
+        RT(c, rt_sync(c->stream));
+        rt_free(c->prop);
+        c->prop = nullptr;
+    }
+    if (kernel) {
+        const size_t S = (size_t)c->h * c->w;
+        int e = dev_alloc(c, &c->prop, S);
+        if (e) return e;
+        RT(c, rt_h2d(c->prop, kernel, S * sizeof(float), c->stream));
+    }
+    c->ff_valid = false;
+    return SLMGS_OK;
+}
+extern "C" int slmgs_set_target(slmgs_ctx* c, const float* target, int shared) {
+    CHECK_CTX(c);
+    if (!target) return fail(c, SLMGS_ERR_INVALID, "target is NULL");
+    c->target_shared = shared ? 1 : 0;
+    return upload_rolled(c, target, c->target, shared ? 1 : c->B);
+}
+extern "C" int slmgs_get_target(slmgs_ctx* c, float* target) {
+    CHECK_CTX(c);
+    if (!target) return fail(c, SLMGS_ERR_INVALID, "target is NULL");
+    return download_rolled(c, c->target, target, c->target_shared ? 1 : c->B);
+}
+extern "C" int slmgs_reset_weights(slmgs_ctx* c) {
+    CHECK_CTX(c);
+    const long long P = (long long)c->H * c->W;
+    ElemArgs a = elem_args(c, c->target, c->weights, P);
+    a.src_bs = c->target_shared ? 0 : P;
+    c->w_pending = -1;
+    return launch_elem<EW_FILL_NAN0>(c, a, c->B);
+}
+extern "C" int slmgs_set_weights(slmgs_ctx* c, const float* weights) {
+    CHECK_CTX(c);
+    if (!weights) return fail(c, SLMGS_ERR_INVALID, "weights is NULL");
+    c->w_pending = -1;
+    return upload_rolled(c, weights, c->weights, c->B);
+}
+extern "C" int slmgs_get_weights(slmgs_ctx* c, float* weights) {
+    CHECK_CTX(c);
+    if (!weights) return fail(c, SLMGS_ERR_INVALID, "weights is NULL");
+    int e = resolve_weights(c);
+    if (e) return e;
+    return download_rolled(c, c->weights, weights, c->B);
+}
+extern "C" int slmgs_set_phase_ff(slmgs_ctx* c, const float* p) {
+    CHECK_CTX(c);
+    if (!p) return fail(c, SLMGS_ERR_INVALID, "phase_ff is NULL");
+    return upload_rolled(c, p, c->phase_ff, c->B);
+}
+extern "C" int slmgs_get_phase_ff(slmgs_ctx* c, float* p) {
+    CHECK_CTX(c);
+    if (!p) return fail(c, SLMGS_ERR_INVALID, "phase_ff is NULL");
+    return download_rolled(c, c->phase_ff, p, c->B);
+}
+extern "C" int slmgs_get_amp_ff(slmgs_ctx* c, float* p) {
+    CHECK_CTX(c);
+    if (!p) return fail(c, SLMGS_ERR_INVALID, "amp_ff is NULL");
+    return download_rolled(c, c->amp_ff, p, c->B);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel argument builders
+// ------------------------------------------------------------------------------------------
+static RowArgs row_args(slmgs_ctx* c) {
+    RowArgs a;
+    memset(&a, 0, sizeof a);
+    a.fld = c->fld;
+    a.fld_bs = (long long)c->H * c->W;
+    a.phase = c->phase;
+    a.phase_bs = (long long)c->h * c->w;
+    a.amp = c->amp;
+    a.amp_bs = c->amp_per_hologram ? (long long)c->h * c->w : 0;
+    a.prop = c->prop;
+    a.nearfield = nullptr;
+    a.twA = c->twA_row;
+    a.twB = c->twB_row;
+    a.amp_scalar = c->amp_scalar;
+    a.scale = (float)(1.0 / sqrt((double)c->H * (double)c->W));
+    a.H = c->H; a.W = c->W; a.h = c->h; a.w = c->w; a.i0 = c->i0; a.i2 = c->i2;
+    a.store_phase = 0;
+    return a;
+}
+static ColArgs col_args(slmgs_ctx* c) {
+    ColArgs a;
+    memset(&a, 0, sizeof a);
+    a.fld = c->fld;
+    a.fld_bs = (long long)c->H * c->W;
+    a.twA = c->twA_col;
+    a.twB = c->twB_col;
+    a.weights = c->weights;
+    a.target = c->target;
+    a.phase_ff = c->phase_ff;
+    a.amp_ff = c->amp_ff;
+    a.farfield = c->farfield;
+    a.img_bs = (long long)c->H * c->W;
+    a.target_bs = c->target_shared ? 0 : a.img_bs;
+    a.acc = c->acc;
+    a.acc_bs = ACC_N;
+    a.w_in_slot = -1;
+    a.w_out_slot = -1;
+    a.H = c->H; a.W = c->W; a.h = c->h; a.i0 = c->i0;
+    a.scale = (float)(1.0 / sqrt((double)c->H * (double)c->W));
+    a.wgs.method = METHOD_GS;
+    a.wgs.p = 0.f; a.wgs.f = 0.f;
+    a.wgs.inv_fnorm = (float)(1.0 / c->fnorm);
+    a.wgs.neg_inv_mean = -1.0f;
+    return a;
+}
+// profiling: bracket a launch with events from a pool (class k: 0..2 row modes, 3..5 column modes)
+static void prof_mark(slmgs_ctx* c, int klass, bool begin) {
+#ifndef SLMGS_EMULATE
+    if (!c->profiling) return;
+    if (c->ev_used == c->ev_pool.size()) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        c->ev_pool.push_back(e);
+    }
+    if (begin) c->ev_class.push_back(klass);
+    cudaEventRecord(c->ev_pool[c->ev_used++], c->stream);
+#else
+    (void)c; (void)klass; (void)begin;
+#endif
+}
+static int run_row(slmgs_ctx* c, int mode, const RowArgs& a) {
+    c->launches++;
+    prof_mark(c, mode, true);
+    int e = rt_check(c, launch_row(c->W, mode, c->row_gx, c->B, c->row_threads, c->stream, a), "row kernel launch");
+    prof_mark(c, mode, false);
+    return e;
+}
+static int run_col(slmgs_ctx* c, int mode, const ColArgs& a) {
+    c->launches++;
+    prof_mark(c, 3 + mode, true);
+    int e = rt_check(c, launch_col(c->H, mode, c->col_gx, c->B, c->col_threads, c->stream, a), "column kernel launch");
+    prof_mark(c, 3 + mode, false);
+    return e;
+}
+static int ensure_farfield(slmgs_ctx* c) {
+    if (c->farfield) return 0;
+    return dev_alloc(c, &c->farfield, (size_t)c->B * c->H * c->W);
+}
+static void apply_params(ColArgs& a, const slmgs_params* p) {
+    a.wgs.method = p->method;
+    a.wgs.p = p->feedback_exponent;
+    a.wgs.f = p->feedback_factor;
+    a.phase_mode = p->phase_mode;
+    a.mraf = p->mraf;
+    a.mraf_has_factor = p->mraf_has_factor;
+    a.mraf_factor = p->mraf_factor;
+}
+static int check_params(slmgs_ctx* c, const slmgs_params* p) {
+    if (!p) return fail(c, SLMGS_ERR_INVALID, "params is NULL");
+    if (p->method < SLMGS_GS || p->method > SLMGS_WGS_TANH) return fail(c, SLMGS_ERR_INVALID, "unknown method");
+    if (p->phase_mode < 0 || p->phase_mode > 2) return fail(c, SLMGS_ERR_INVALID, "unknown phase_mode");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused loop
+// ------------------------------------------------------------------------------------------
+extern "C" int slmgs_run(slmgs_ctx* c, const slmgs_params* params, int n_iter, int populate) {
+    CHECK_CTX(c);
+    if (n_iter < 0) return fail(c, SLMGS_ERR_INVALID, "n_iter < 0");
+    if (n_iter > 0 && !params) return fail(c, SLMGS_ERR_INVALID, "params is NULL");
+    for (int i = 0; i < n_iter; ++i) {
+        int e = check_params(c, params + i);
+        if (e) return e;
+        if (params[i].update_weights) {
+            if (params[i].method == SLMGS_GS) return fail(c, SLMGS_ERR_INVALID, "GS has no weight update");
+            if (params[i].method == SLMGS_WGS_NOGRETTE)
+                return fail(c, SLMGS_ERR_INVALID, "WGS-Nogrette needs a global mean: use the stepped entry points");
+            if (params[i].mraf)
+                return fail(c, SLMGS_ERR_INVALID, "MRAF with a weight update needs normalised weights: use the stepped entry points");
+        }
+    }
+    int e;
+    if (n_iter > 0) {
+        RowArgs ra = row_args(c);
+        if ((e = run_row(c, ROW_FIRST, ra))) return e;
+        for (int i = 0; i < n_iter; ++i) {
+            ColArgs ca = col_args(c);
+            apply_params(ca, params + i);
+            ca.wgs_update = params[i].update_weights;
+            ca.w_in_slot = c->w_pending;
+            if (ca.wgs_update) {
+                ca.w_out_slot = (c->w_pending == ACC_W0) ? ACC_W1 : ACC_W0;
+                if ((e = zero_slot(c, ca.w_out_slot))) return e;
+            }
+            if ((e = run_col(c, COL_FUSED, ca))) return e;
+            if (ca.wgs_update) c->w_pending = ca.w_out_slot;
+            ra.store_phase = (i == n_iter - 1);
+            if ((e = run_row(c, ROW_FUSED, ra))) return e;
+        }
+    }
+    c->ff_valid = false;
+    if (populate) return slmgs_populate(c);
+    return SLMGS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// stepped loop
+// ------------------------------------------------------------------------------------------
+static int forward_impl(slmgs_ctx* c, int store_ff, int store_amp, int store_phase, bool first_row) {
+    int e;
+    if (store_ff && (e = ensure_farfield(c))) return e;
+    if (first_row) {
+        RowArgs ra = row_args(c);
+        if ((e = run_row(c, ROW_FIRST, ra))) return e;
+    }
+    ColArgs ca = col_args(c);
+    ca.store_farfield = store_ff;
+    ca.store_ampff = store_amp;
+    ca.store_phaseff = store_phase;
+    return run_col(c, COL_FWD, ca);
+}
+
+extern "C" int slmgs_forward(slmgs_ctx* c) {
+    CHECK_CTX(c);
+    int e = forward_impl(c, 1, 1, 0, true);
+    if (e) return e;
+    c->ff_valid = true;
+    return SLMGS_OK;
+}
+
+extern "C" int slmgs_populate(slmgs_ctx* c) {
+    CHECK_CTX(c);
+    // after a fused run `fld` already holds the row transform of the new near field only if the last
+    // kernel was ROW_FUSED; rebuilding from the stored phase is always valid and costs one row pass.
+    int e = forward_impl(c, c->farfield ? 1 : 0, 1, 1, true);
+    if (e) return e;
+    c->ff_valid = c->farfield != nullptr;
+    return SLMGS_OK;
+}
+
+extern "C" int slmgs_get_farfield(slmgs_ctx* c, float* out) {
+    CHECK_CTX(c);
+    if (!out) return fail(c, SLMGS_ERR_INVALID, "farfield is NULL");
+    int e;
+    if (!c->ff_valid) {
+        if ((e = forward_impl(c, 1, 1, 0, true))) return e;
+        c->ff_valid = true;
+    }
+    const long long P = (long long)c->H * c->W;
+    if (!c->stage_c && (e = dev_alloc(c, &c->stage_c, (size_t)c->B * P))) return e;
+    ElemArgs a = elem_args(c, c->farfield, c->stage_c, P);
+    if ((e = launch_elem<EW_ROLL_C64>(c, a, c->B))) return e;
+    RT(c, rt_d2h(out, c->stage_c, (size_t)c->B * P * sizeof(cf), c->stream));
+    return SLMGS_OK;
+}
+
+extern "C" int slmgs_update_weights(slmgs_ctx* c, const slmgs_params* p) {
+    CHECK_CTX(c);
+    int e = check_params(c, p);
+    if (e) return e;
+    if (p->method == SLMGS_GS) return fail(c, SLMGS_ERR_INVALID, "Weighting is only for WGS.");
+    if (!c->ff_valid) return fail(c, SLMGS_ERR_STATE, "update_weights needs a preceding forward()");
+    if ((e = resolve_weights(c))) return e;
+    const long long P = (long long)c->H * c->W;
+    // ||feedback||, _hologram.py:1830-1831
+    if ((e = zero_slot(c, ACC_FNORM, 2))) return e;  // FNORM and MEAN
+    ElemArgs a = elem_args(c, c->amp_ff, nullptr, P);
+    a.slot0 = ACC_FNORM;
+    if ((e = launch_elem<EW_SUMSQ>(c, a, c->B))) return e;
+    WgsParams q;
+    q.method = p->method; q.p = p->feedback_exponent; q.f = p->feedback_factor; q.inv_fnorm = 1.f; q.neg_inv_mean = -1.f;
+    if (p->method == SLMGS_WGS_NOGRETTE) {
+        ElemArgs m = elem_args(c, c->amp_ff, nullptr, P);
+        m.wgs = q; m.fnorm_slot = ACC_FNORM; m.slot0 = ACC_MEAN;
+        if ((e = launch_elem<EW_RATIO_SUM>(c, m, c->B))) return e;
+    }
+    if ((e = zero_slot(c, ACC_W0))) return e;
+    ElemArgs u = elem_args(c, c->amp_ff, c->weights, P);
+    u.wgs = q; u.fnorm_slot = ACC_FNORM; u.mean_slot = (p->method == SLMGS_WGS_NOGRETTE) ? ACC_MEAN : -1; u.slot1 = ACC_W0;
+    if ((e = launch_elem<EW_WGS_UPDATE>(c, u, c->B))) return e;
+    ElemArgs s = elem_args(c, nullptr, c->weights, P);
+    s.slot0 = ACC_W0;
+    return launch_elem<EW_SCALE>(c, s, c->B);
+}
+
+extern "C" int slmgs_set_spots(slmgs_ctx* c, int n, const int* x, const int* y, const float* spot_amp) {
+    CHECK_CTX(c);
+    if (n < 1 || !x || !y || !spot_amp) return fail(c, SLMGS_ERR_INVALID, "bad spot arguments");
+    for (int i = 0; i < n; ++i)
+        if (x[i] < 0 || x[i] >= c->W || y[i] < 0 || y[i] >= c->H) return fail(c, SLMGS_ERR_INVALID, "spot outside the computational space");
+    RT(c, rt_sync(c->stream));
+    if (c->spot_x) { rt_free(c->spot_x); rt_free(c->spot_y); rt_free(c->spot_amp); rt_free(c->spot_pw); c->spot_x = nullptr; }
+    int e;
+    if ((e = dev_alloc(c, &c->spot_x, (size_t)n))) return e;
+    if ((e = dev_alloc(c, &c->spot_y, (size_t)n))) return e;
+    if ((e = dev_alloc(c, &c->spot_amp, (size_t)n))) return e;
+    if ((e = dev_alloc(c, &c->spot_pw, (size_t)n * c->B))) return e;
+    RT(c, rt_h2d(c->spot_x, x, (size_t)n * sizeof(int), c->stream));
+    RT(c, rt_h2d(c->spot_y, y, (size_t)n * sizeof(int), c->stream));
+    RT(c, rt_h2d(c->spot_amp, spot_amp, (size_t)n * sizeof(float), c->stream));
+    c->n_spots = n;
+    return SLMGS_OK;
+}
+
+static SpotArgs spot_args(slmgs_ctx* c, int width) {
+    SpotArgs a;
+    memset(&a, 0, sizeof a);
+    a.img = c->amp_ff; a.weights = c->weights; a.sx = c->spot_x; a.sy = c->spot_y; a.spot_amp = c->spot_amp;
+    a.pw = c->spot_pw; a.img_bs = (long long)c->H * c->W; a.H = c->H; a.W = c->W; a.N = c->n_spots; a.width = width;
+    return a;
+}
+
+extern "C" int slmgs_update_weights_spot(slmgs_ctx* c, const slmgs_params* p, int width) {
+    CHECK_CTX(c);
+    int e = check_params(c, p);
+    if (e) return e;
+    if (p->method == SLMGS_GS) return fail(c, SLMGS_ERR_INVALID, "Weighting is only for WGS.");
+    if (c->n_spots < 1) return fail(c, SLMGS_ERR_STATE, "no spots set");
+    if (width < 1) return fail(c, SLMGS_ERR_INVALID, "width < 1");
+    if (!c->ff_valid) return fail(c, SLMGS_ERR_STATE, "update_weights_spot needs a preceding forward()");
+    if ((e = resolve_weights(c))) return e;
+    SpotArgs a = spot_args(c, width);
+    a.wgs.method = p->method; a.wgs.p = p->feedback_exponent; a.wgs.f = p->feedback_factor;
+    a.wgs.inv_fnorm = 1.f; a.wgs.neg_inv_mean = -1.f;
+    c->launches++;
+    e = rt_check(c, launch_kernel<SpotGatherKernel>((c->n_spots + 255) / 256, c->B, 256, 0, c->stream, a), "spot gather launch");
+    if (e) return e;
+    c->launches++;
+    return rt_check(c, launch_kernel<SpotUpdateKernel>(1, c->B, 1024, (1024 + 8) * sizeof(double), c->stream, a), "spot update launch");
+}
+
+extern "C" int slmgs_constrain_inverse(slmgs_ctx* c, const slmgs_params* p) {
+    CHECK_CTX(c);
+    int e = check_params(c, p);
+    if (e) return e;
+    if (!c->ff_valid || !c->farfield) return fail(c, SLMGS_ERR_STATE, "constrain_inverse needs a preceding forward()");
+    if ((e = resolve_weights(c))) return e;
+    ColArgs ca = col_args(c);
+    apply_params(ca, p);
+    ca.wgs_update = 0;
+    if ((e = run_col(c, COL_INV, ca))) return e;
+    RowArgs ra = row_args(c);
+    if ((e = run_row(c, ROW_LAST, ra))) return e;
+    c->ff_valid = false;
+    return SLMGS_OK;
+}
+
+extern "C" int slmgs_get_nearfield(slmgs_ctx* c, float* out) {
+    CHECK_CTX(c);
+    if (!out) return fail(c, SLMGS_ERR_INVALID, "nearfield is NULL");
+    return fail(c, SLMGS_ERR_STATE, "nearfield download is not kept by the fused loop; rebuild it from get_phase() and amp");
+}
+
+// ------------------------------------------------------------------------------------------
+// statistics
+// ------------------------------------------------------------------------------------------
+extern "C" int slmgs_stats_pixel(slmgs_ctx* c, double* out8, double* out2) {
+    CHECK_CTX(c);
+    if (!out8 || !out2) return fail(c, SLMGS_ERR_INVALID, "output is NULL");
+    int e;
+    const long long P = (long long)c->H * c->W;
+    if ((e = zero_slot(c, ACC_S0, 3))) return e;
+    ElemArgs a = elem_args(c, c->amp_ff, nullptr, P);
+    a.slot0 = ACC_S0; a.slot1 = ACC_S1; a.slot2 = ACC_S2;
+    if ((e = launch_elem<EW_STATS1>(c, a, c->B))) return e;
+    Stats2Args s;
+    memset(&s, 0, sizeof s);
+    s.f = c->amp_ff; s.t = c->target; s.partial = c->partial; s.acc = c->acc; s.n = P; s.f_bs = P;
+    s.t_bs = c->target_shared ? 0 : P; s.acc_bs = ACC_N; s.fsum_slot = ACC_S0; s.tsum_slot = ACC_S1;
+    const int gx = 256;
+    c->launches++;
+    e = rt_check(c, launch_kernel<Stats2Kernel>(gx, c->B, 256, 256 * 8 * sizeof(double), c->stream, s), "stats launch");
+    if (e) return e;
+    std::vector<double> part((size_t)c->B * gx * 8), acc((size_t)c->B * ACC_N);
+    RT(c, rt_d2h(part.data(), c->partial, part.size() * sizeof(double), c->stream));
+    RT(c, rt_d2h(acc.data(), c->acc, acc.size() * sizeof(double), c->stream));
+    for (int b = 0; b < c->B; ++b) {
+        double r[7] = {INFINITY, -INFINITY, INFINITY, -INFINITY, 0, 0, 0};
+        for (int g = 0; g < gx; ++g) {
+            const double* o = &part[((size_t)b * gx + g) * 8];
+            if (o[0] < r[0]) r[0] = o[0];
+            if (o[1] > r[1]) r[1] = o[1];
+            if (o[2] < r[2]) r[2] = o[2];
+            if (o[3] > r[3]) r[3] = o[3];
+            r[4] += o[4]; r[5] += o[5]; r[6] += o[6];
+        }
+        double* o8 = out8 + (size_t)b * 8;
+        o8[0] = acc[(size_t)b * ACC_N + ACC_S0];
+        o8[1] = acc[(size_t)b * ACC_N + ACC_S1];
+        o8[2] = acc[(size_t)b * ACC_N + ACC_S2];
+        o8[3] = r[0]; o8[4] = r[1]; o8[5] = r[2]; o8[6] = r[3]; o8[7] = r[4];
+        out2[(size_t)b * 2 + 0] = r[5];
+        out2[(size_t)b * 2 + 1] = r[6];
+    }
+    return SLMGS_OK;
+}
+
+extern "C" int slmgs_window_power(slmgs_ctx* c, int n, const int* x, const int* y, int width, double* out, double* total) {
+    CHECK_CTX(c);
+    if (n < 1 || !x || !y || !out || width < 1) return fail(c, SLMGS_ERR_INVALID, "bad window_power arguments");
+    for (int i = 0; i < n; ++i) {
+        const int lo = (width & 1) ? -((width - 1) / 2) : -(width / 2), hi = lo + width - 1;
+        // NumPy fancy indexing: negative indices wrap once, indices past the end raise IndexError
+        if (x[i] + lo < -c->W || x[i] + hi >= c->W || y[i] + lo < -c->H || y[i] + hi >= c->H)
+            return fail(c, SLMGS_ERR_INVALID, "index out of bounds in window integration");
+    }
+    int e;
+    int *dx = nullptr, *dy = nullptr;
+    double* dpw = nullptr;
+    if ((e = dev_alloc(c, &dx, (size_t)n))) return e;
+    if ((e = dev_alloc(c, &dy, (size_t)n))) { rt_free(dx); return e; }
+    if ((e = dev_alloc(c, &dpw, (size_t)n * c->B))) { rt_free(dx); rt_free(dy); return e; }
+    e = rt_check(c, rt_h2d(dx, x, (size_t)n * sizeof(int), c->stream), "h2d");
+    if (!e) e = rt_check(c, rt_h2d(dy, y, (size_t)n * sizeof(int), c->stream), "h2d");
+    if (!e) {
+        SpotArgs a = spot_args(c, width);
+        a.sx = dx; a.sy = dy; a.pw = dpw; a.N = n;
+        c->launches++;
+        e = rt_check(c, launch_kernel<SpotGatherKernel>((n + 255) / 256, c->B, 256, 0, c->stream, a), "spot gather launch");
+    }
+    if (!e) e = rt_check(c, rt_d2h(out, dpw, (size_t)n * c->B * sizeof(double), c->stream), "d2h");
+    if (!e && total) {
+        e = zero_slot(c, ACC_TMP);
+        if (!e) {
+            ElemArgs s = elem_args(c, c->amp_ff, nullptr, (long long)c->H * c->W);
+            s.slot0 = ACC_TMP;
+            e = launch_elem<EW_SUMSQ>(c, s, c->B);
+        }
+        std::vector<double> acc((size_t)c->B * ACC_N);
+        if (!e) e = rt_check(c, rt_d2h(acc.data(), c->acc, acc.size() * sizeof(double), c->stream), "d2h");
+        if (!e)
+            for (int b = 0; b < c->B; ++b) total[b] = acc[(size_t)b * ACC_N + ACC_TMP];
+    }
+    rt_sync(c->stream);
+    rt_free(dx); rt_free(dy); rt_free(dpw);
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel timing (bench / roofline): CUDA events on the launching stream
+// ------------------------------------------------------------------------------------------
+extern "C" int slmgs_time_kernel(slmgs_ctx* c, int which, int n, float* ms_out) {
+    CHECK_CTX(c);
+    if (n < 1 || !ms_out) return fail(c, SLMGS_ERR_INVALID, "bad time_kernel arguments");
+#ifdef SLMGS_EMULATE
+    *ms_out = 0.f;
+    return fail(c, SLMGS_ERR_STATE, "kernel timing needs a GPU");
+#else
+    cudaEvent_t e0, e1;
+    RT(c, (int)cudaEventCreate(&e0));
+    RT(c, (int)cudaEventCreate(&e1));
+    RowArgs ra = row_args(c);
+    ColArgs ca = col_args(c);
+    ca.store_ampff = 1; ca.store_phaseff = 1;
+    int e = 0;
+    // one untimed launch first (instruction cache, attribute set-up)
+    for (int i = -1; i < n && !e; ++i) {
+        if (i == 0) e = rt_check(c, (int)cudaEventRecord(e0, c->stream), "event record");
+        if (e) break;
+        switch (which) {
+            case 0: e = run_row(c, ROW_FUSED, ra); break;
+            case 1: e = run_col(c, COL_FUSED, ca); break;
+            case 2: e = run_row(c, ROW_FIRST, ra); break;
+            case 3: e = run_col(c, COL_FWD, ca); break;
+            default: e = fail(c, SLMGS_ERR_INVALID, "unknown kernel selector");
+        }
+    }
+    if (!e) e = rt_check(c, (int)cudaEventRecord(e1, c->stream), "event record");
+    if (!e) e = rt_check(c, (int)cudaEventSynchronize(e1), "event sync");
+    float ms = 0.f;
+    if (!e) e = rt_check(c, (int)cudaEventElapsedTime(&ms, e0, e1), "event elapsed");
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_out = ms / (float)n;
+    c->ff_valid = false;
+    return e;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
+// phase snapshot, timers, per-kernel profile
+// ------------------------------------------------------------------------------------------
+extern "C" int slmgs_save_phase(slmgs_ctx* c) {
+    CHECK_CTX(c);
+    const size_t n = (size_t)c->B * c->h * c->w;
+    int e;
+    if (!c->phase_saved && (e = dev_alloc(c, &c->phase_saved, n))) return e;
+#ifdef SLMGS_EMULATE
+    memcpy(c->phase_saved, c->phase, n * sizeof(float));
+#else
+    RT(c, (int)cudaMemcpyAsync(c->phase_saved, c->phase, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+#endif
+    return SLMGS_OK;
+}
+extern "C" int slmgs_restore_phase(slmgs_ctx* c) {
+    CHECK_CTX(c);
+    if (!c->phase_saved) return fail(c, SLMGS_ERR_STATE, "restore_phase without save_phase");
+    const size_t n = (size_t)c->B * c->h * c->w;
+#ifdef SLMGS_EMULATE
+    memcpy(c->phase, c->phase_saved, n * sizeof(float));
+#else
+    RT(c, (int)cudaMemcpyAsync(c->phase, c->phase_saved, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+#endif
+    c->ff_valid = false;
+    return SLMGS_OK;
+}
+extern "C" int slmgs_timer_start(slmgs_ctx* c) {
+    CHECK_CTX(c);
+#ifndef SLMGS_EMULATE
+    if (!c->t0) {
+        RT(c, (int)cudaEventCreate(&c->t0));
+        RT(c, (int)cudaEventCreate(&c->t1));
+    }
+    RT(c, (int)cudaEventRecord(c->t0, c->stream));
+#endif
+    return SLMGS_OK;
+}
+extern "C" int slmgs_timer_stop(slmgs_ctx* c, float* ms) {
+    CHECK_CTX(c);
+    if (!ms) return fail(c, SLMGS_ERR_INVALID, "ms is NULL");
+    *ms = 0.f;
+#ifndef SLMGS_EMULATE
+    if (!c->t0) return fail(c, SLMGS_ERR_STATE, "timer_stop without timer_start");
+    RT(c, (int)cudaEventRecord(c->t1, c->stream));
+    RT(c, (int)cudaEventSynchronize(c->t1));
+    RT(c, (int)cudaEventElapsedTime(ms, c->t0, c->t1));
+#endif
+    return SLMGS_OK;
+}
+extern "C" int slmgs_profile_enable(slmgs_ctx* c, int on) {
+    CHECK_CTX(c);
+    c->profiling = on != 0;
+#ifndef SLMGS_EMULATE
+    c->ev_used = 0;
+    c->ev_class.clear();
+#endif
+    return SLMGS_OK;
+}
+extern "C" int slmgs_profile_read(slmgs_ctx* c, float* ms6, int* count6) {
+    CHECK_CTX(c);
+    if (!ms6 || !count6) return fail(c, SLMGS_ERR_INVALID, "output is NULL");
+    for (int k = 0; k < 6; ++k) { ms6[k] = 0.f; count6[k] = 0; }
+#ifndef SLMGS_EMULATE
+    RT(c, rt_sync(c->stream));
+    for (size_t i = 0; i < c->ev_class.size() && 2 * i + 1 < c->ev_used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev_pool[2 * i], c->ev_pool[2 * i + 1]) == cudaSuccess) {
+            ms6[c->ev_class[i]] += ms;
+            count6[c->ev_class[i]]++;
+        }
+    }
+    c->ev_used = 0;
+    c->ev_class.clear();
+#endif
+    return SLMGS_OK;
+}

@@ -1,0 +1,165 @@
+// slmgs_common.h -- shared device / host-emulation primitives for the GS/WGS hot path.
+//
+// Every kernel in this library is written as a sequence of barrier-delimited "phases"
+// (see slmgs_launch.h).  Under nvcc the phases are chained with __syncthreads() inside one
+// sm_100a kernel.  Under a plain C++ compiler with -DSLMGS_EMULATE the very same phase
+// functions are executed by a host loop over (block, phase, thread): that build is TEST
+// INFRASTRUCTURE (tests/_emu) used to validate index math and arithmetic without a GPU;
+// the product library (libslmgs.so) never contains it.
+#pragma once
+
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__) && !defined(SLMGS_EMULATE)
+#define SLMGS_DEVICE __device__ __forceinline__
+#define SLMGS_HD __host__ __device__ __forceinline__
+#define SLMGS_RESTRICT __restrict__
+#define SLMGS_UNROLL _Pragma("unroll")
+#else
+#ifndef SLMGS_EMULATE
+#define SLMGS_EMULATE 1
+#endif
+#define SLMGS_DEVICE inline
+#define SLMGS_HD inline
+#define SLMGS_RESTRICT
+#define SLMGS_UNROLL
+struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+static inline void sincosf_emu(float a, float* s, float* c) { *s = sinf(a); *c = cosf(a); }
+#define sincosf(a, s, c) sincosf_emu(a, s, c)
+template <class T> static inline T __ldg(const T* p) { return *p; }
+#endif
+
+namespace slmgs {
+
+typedef float2 cf;  // complex float, (re, im)
+
+SLMGS_HD cf cmake(float re, float im) { return make_float2(re, im); }
+SLMGS_HD cf cadd(cf a, cf b) { return make_float2(a.x + b.x, a.y + b.y); }
+SLMGS_HD cf csub(cf a, cf b) { return make_float2(a.x - b.x, a.y - b.y); }
+SLMGS_HD cf cmul(cf a, cf b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// a * conj(b)
+SLMGS_HD cf cmulc(cf a, cf b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
+SLMGS_HD cf cscale(cf a, float s) { return make_float2(a.x * s, a.y * s); }
+// a * w (DIR=+1) or a * conj(w) (DIR=-1)
+template <int DIR> SLMGS_HD cf cmul_dir(cf a, cf w) { return DIR > 0 ? cmul(a, w) : cmulc(a, w); }
+// multiply by -i (DIR=+1, forward) or +i (DIR=-1, inverse)
+template <int DIR> SLMGS_HD cf cmul_mi(cf a) {
+    return DIR > 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
+}
+
+// ---------------------------------------------------------------------------------------
+// 32nd roots of unity, cos(2 pi k / 32), k = 0..8, correctly rounded to fp32.  In-register
+// butterflies only need constants up to radix 32.
+// ---------------------------------------------------------------------------------------
+constexpr float root32_tab(int j) {
+    return j == 0 ? 1.0f : j == 1 ? 0.98078528040323043f : j == 2 ? 0.92387953251128674f
+         : j == 3 ? 0.83146961230254524f : j == 4 ? 0.70710678118654757f : j == 5 ? 0.55557023301960218f
+         : j == 6 ? 0.38268343236508978f : j == 7 ? 0.19509032201612825f : 0.0f;
+}
+constexpr float root32_cos(int k) {
+    return k <= 8 ? root32_tab(k) : k <= 16 ? -root32_tab(16 - k) : k <= 24 ? -root32_tab(k - 16) : root32_tab(32 - k);
+}
+constexpr float root32_sin(int k) {
+    return k <= 8 ? root32_tab(8 - k) : k <= 16 ? root32_tab(k - 8) : k <= 24 ? -root32_tab(24 - k) : -root32_tab(k - 24);
+}
+
+// v * exp(-i * DIR * 2 pi E / R)   (compile-time constant twiddle; trivial cases folded)
+template <int DIR, int R, int E> SLMGS_HD cf ctwiddle_const(cf v) {
+    constexpr int k = ((E * (32 / R)) % 32 + 32) % 32;
+    if (k == 0) return v;
+    if (k == 8) return cmul_mi<DIR>(v);
+    if (k == 16) return make_float2(-v.x, -v.y);
+    if (k == 24) return cmul_mi<-DIR>(v);
+    constexpr float c = root32_cos(k);
+    constexpr float s = DIR > 0 ? -root32_sin(k) : root32_sin(k);
+    if (k == 4 || k == 12 || k == 20 || k == 28) {
+        // |c| == |s| == sqrt(1/2): two adds + two multiplies
+        constexpr float q = 0.70710678118654757f;
+        constexpr float sc = c > 0 ? 1.0f : -1.0f, ss = s > 0 ? 1.0f : -1.0f;
+        // (x + i y)(c + i s) = (x c - y s) + i (x s + y c)
+        return make_float2((sc * v.x - ss * v.y) * q, (ss * v.x + sc * v.y) * q);
+    }
+    return make_float2(v.x * c - v.y * s, v.x * s + v.y * c);
+}
+
+// ---------------------------------------------------------------------------------------
+// In-register DFT of R points (R = 1, 2, 4, 8, 16, 32), decimation in frequency.  Input in
+// natural order in v[0], v[S], v[2S], ...  Output: frequency k lives in v[S * pos(k)].
+// DIR=+1: forward kernel exp(-i...), DIR=-1: inverse kernel exp(+i...).  Unnormalised.
+// ---------------------------------------------------------------------------------------
+template <int R> struct RegFFT;
+
+template <> struct RegFFT<1> {
+    static constexpr int pos(int k) { return k; }
+    template <int DIR, int S> static SLMGS_HD void run(cf*) {}
+};
+
+template <> struct RegFFT<2> {
+    static constexpr int pos(int k) { return k; }
+    template <int DIR, int S> static SLMGS_HD void run(cf* v) {
+        cf a = v[0], b = v[S];
+        v[0] = cadd(a, b);
+        v[S] = csub(a, b);
+    }
+};
+
+template <> struct RegFFT<4> {
+    static constexpr int pos(int k) { return k; }
+    template <int DIR, int S> static SLMGS_HD void run(cf* v) {
+        cf a = v[0], b = v[S], c = v[2 * S], d = v[3 * S];
+        cf t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = cmul_mi<DIR>(csub(b, d));
+        v[0] = cadd(t0, t2);
+        v[S] = cadd(t1, t3);
+        v[2 * S] = csub(t0, t2);
+        v[3 * S] = csub(t1, t3);
+    }
+};
+
+// R = 4 * M: radix-4 over elements (j, j+M, j+2M, j+3M), twiddle, then M-point DFTs on
+// each contiguous block of M.  X[k0 + 4 k'] sits at k0*M + RegFFT<M>::pos(k').
+template <int R> struct RegFFT {
+    static constexpr int M = R / 4;
+    static constexpr int pos(int k) { return (k % 4) * M + RegFFT<M>::pos(k / 4); }
+
+    template <int DIR, int S, int J> static SLMGS_HD void first(cf* v) {
+        if constexpr (J < M) {
+            RegFFT<4>::template run<DIR, S * M>(v + J * S);
+            v[(J + M) * S] = ctwiddle_const<DIR, R, J>(v[(J + M) * S]);
+            v[(J + 2 * M) * S] = ctwiddle_const<DIR, R, 2 * J>(v[(J + 2 * M) * S]);
+            v[(J + 3 * M) * S] = ctwiddle_const<DIR, R, 3 * J>(v[(J + 3 * M) * S]);
+            first<DIR, S, J + 1>(v);
+        }
+    }
+    template <int DIR, int S> static SLMGS_HD void run(cf* v) {
+        first<DIR, S, 0>(v);
+        RegFFT<M>::template run<DIR, S>(v);
+        RegFFT<M>::template run<DIR, S>(v + M * S);
+        RegFFT<M>::template run<DIR, S>(v + 2 * M * S);
+        RegFFT<M>::template run<DIR, S>(v + 3 * M * S);
+    }
+};
+
+template <> struct RegFFT<8> {
+    // 8 = 2 * 4: radix-2 over (j, j+4), twiddle w8^j on the odd half, then two 4-point DFTs.
+    // X[k0 + 2 k'] at k0*4 + k'
+    static constexpr int pos(int k) { return (k % 2) * 4 + (k / 2); }
+    template <int DIR, int S> static SLMGS_HD void run(cf* v) {
+        cf a0 = v[0], a1 = v[S], a2 = v[2 * S], a3 = v[3 * S];
+        cf b0 = v[4 * S], b1 = v[5 * S], b2 = v[6 * S], b3 = v[7 * S];
+        v[0] = cadd(a0, b0);
+        v[S] = cadd(a1, b1);
+        v[2 * S] = cadd(a2, b2);
+        v[3 * S] = cadd(a3, b3);
+        v[4 * S] = csub(a0, b0);
+        v[5 * S] = ctwiddle_const<DIR, 8, 1>(csub(a1, b1));
+        v[6 * S] = ctwiddle_const<DIR, 8, 2>(csub(a2, b2));
+        v[7 * S] = ctwiddle_const<DIR, 8, 3>(csub(a3, b3));
+        RegFFT<4>::template run<DIR, S>(v);
+        RegFFT<4>::template run<DIR, S>(v + 4 * S);
+    }
+};
+
+}  // namespace slmgs

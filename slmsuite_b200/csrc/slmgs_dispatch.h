@@ -1,0 +1,37 @@
+// slmgs_dispatch.h -- per-size launchers (one translation unit per N, see slmgs_inst.cu).
+#pragma once
+#include "slmgs_kernels.h"
+
+namespace slmgs {
+
+#ifdef SLMGS_EMULATE
+typedef void* rt_stream;
+#else
+typedef cudaStream_t rt_stream;
+#endif
+
+struct LaunchInfo {
+    int E;       // points per thread
+    int tpl;     // threads per line
+    int maxt;    // max threads per block
+    int padn;    // padded line length (complex elements)
+    int ns;      // number of radix stages
+};
+
+#define SLMGS_DECL(N_)                                                                                        \
+    int launch_row_##N_(int mode, int gx, int gy, int nthreads, rt_stream s, const RowArgs& a);               \
+    int launch_col_##N_(int mode, int gx, int gy, int nthreads, rt_stream s, const ColArgs& a);               \
+    LaunchInfo launch_info_##N_();
+SLMGS_DECL(16)
+SLMGS_DECL(32)
+SLMGS_DECL(64)
+SLMGS_DECL(128)
+SLMGS_DECL(256)
+SLMGS_DECL(512)
+SLMGS_DECL(1024)
+SLMGS_DECL(2048)
+SLMGS_DECL(4096)
+SLMGS_DECL(8192)
+#undef SLMGS_DECL
+
+}  // namespace slmgs

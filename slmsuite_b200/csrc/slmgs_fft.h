@@ -1,0 +1,192 @@
+// slmgs_fft.h -- register/shared-memory 1-D FFT of a line of N = R0*R1*R2 points.
+//
+// Data model.  A tile is LINES lines of N points.  Each thread owns E points (E = 16, or 32
+// for N = 8192) in registers for the whole kernel; shared memory is only the exchange medium
+// between radix stages.  A line is served by TPL = N/E threads; "lt" is the thread's index
+// inside its line.  A stage of radix R has N/R butterflies per line; thread lt executes the
+// Q = E/R butterflies b = lt + TPL*u, u = 0..Q-1, keeping butterfly u in v[u*R .. u*R+R-1].
+//
+// Index algebra (n = spatial index, k = frequency index):
+//     n = n0*(R1 R2) + n1*R2 + n2            k = k0 + R0*k1 + R0*R1*k2
+//   stage A (radix R0): butterfly b = j = n1*R2+n2, element m=n0/k0 at line index  m*M1 + j
+//   stage B (radix R1): butterfly b = k0*R2 + n2,   element m=n1/k1 at line index  k0*M1 + m*R2 + n2
+//   stage C (radix R2): butterfly b = k0 + R0*k1,   element m=n2/k2 at line index  k0*M1 + k1*R2 + m
+// with M1 = R1*R2.  Every stage reads and writes the SAME R line positions (in place), so one
+// barrier per stage suffices.  First-stage elements sit at spatial index n = b + (N/R0)*m and
+// last-stage elements at frequency k = b + (N/Rlast)*m, i.e. consecutive threads touch
+// consecutive addresses at both ends: global loads and stores are coalesced straight from
+// registers with no staging pass.
+//
+//   forward:  A, *W_N^{j k0}, B, *W_M1^{n2 k1}, C            (DIF)
+//   inverse:  C^-1, *conj W_M1, B^-1, *conj W_N, A^-1        (exact mirror, DIT)
+// so the inverse consumes exactly the register layout the forward produces and vice versa:
+// forward -> pointwise -> inverse (column kernel) and inverse -> pointwise -> forward (row
+// kernel) chain without any data movement in between.
+//
+// Twiddles come from two small host-computed tables (double precision, rounded once):
+//   twA[k0*M1 + j] = exp(-2 pi i j k0 / N)   (N entries, indexed by the line index itself)
+//   twB[k1*R2 + n2] = exp(-2 pi i n2 k1 / M1) (M1 entries)
+// Consecutive threads read consecutive entries; the tables stay L1 resident.
+#pragma once
+
+#include "slmgs_common.h"
+
+namespace slmgs {
+
+template <int N> struct Plan;
+#define SLMGS_PLAN(N_, E_, A_, B_, C_)                                          \
+    template <> struct Plan<N_> {                                               \
+        static constexpr int E = E_, R0 = A_, R1 = B_, R2 = C_;                 \
+    };
+SLMGS_PLAN(16, 16, 16, 1, 1)
+SLMGS_PLAN(32, 16, 16, 2, 1)
+SLMGS_PLAN(64, 16, 16, 4, 1)
+SLMGS_PLAN(128, 16, 16, 8, 1)
+SLMGS_PLAN(256, 16, 16, 16, 1)
+SLMGS_PLAN(512, 16, 16, 16, 2)
+SLMGS_PLAN(1024, 16, 16, 16, 4)
+SLMGS_PLAN(2048, 16, 16, 16, 8)
+SLMGS_PLAN(4096, 16, 16, 16, 16)
+SLMGS_PLAN(8192, 32, 32, 16, 16)
+#undef SLMGS_PLAN
+
+// Padded shared-memory index: one pad element per 16 and one more per 256.  Makes the three
+// access patterns (consecutive, stride R2, stride M1) hit distinct 8-byte bank pairs within
+// each half-warp for the plans above (DESIGN.md "Shared memory layout").
+SLMGS_HD int padi(int i) { return i + (i >> 4) + (i >> 8); }
+
+template <int N> struct Fft {
+    typedef Plan<N> P;
+    static constexpr int E = P::E, R0 = P::R0, R1 = P::R1, R2 = P::R2;
+    static constexpr int NS = 1 + (R1 > 1) + (R2 > 1);
+    static constexpr int M1 = R1 * R2;
+    static constexpr int TPL = N / E;
+    static constexpr int PADN = N + (N >> 4) + (N >> 8) + 1;
+    static_assert(R0 * R1 * R2 == N, "bad plan");
+
+    template <int S> static constexpr int radix() { return S == 0 ? R0 : S == 1 ? R1 : R2; }
+    static constexpr int last_radix() { return radix<NS - 1>(); }
+
+    // line index of element m of butterfly b at stage S
+    template <int S> static SLMGS_HD int idx(int b, int m) {
+        if (S == 0) return m * M1 + b;
+        if (S == 1) return (b / R2) * M1 + m * R2 + (b % R2);
+        return (b % R0) * M1 + (b / R0) * R2 + m;
+    }
+    // twiddle applied after forward stage S (S < NS-1) to output m of butterfly b
+    template <int S> static SLMGS_DEVICE cf twiddle(const cf* SLMGS_RESTRICT twA, const cf* SLMGS_RESTRICT twB, int b,
+                                                   int m) {
+        if (S == 0) return __ldg(twA + m * M1 + b);
+        return __ldg(twB + m * R2 + (b % R2));
+    }
+    // spatial index of element m of first-stage butterfly b / frequency of element m of last-stage butterfly b
+    static SLMGS_HD int first_index(int b, int m) { return b + (N / R0) * m; }
+    static SLMGS_HD int last_index(int b, int m) { return b + (N / last_radix()) * m; }
+
+    // ---- compile-time loops --------------------------------------------------------------
+    template <int S, int DIR, int U, int K>
+    static SLMGS_DEVICE void fwd_store(cf* v, int lt, const cf* twA, const cf* twB, cf* s, int si) {
+        constexpr int R = radix<S>();
+        if constexpr (K < R) {
+            const int b = lt + TPL * U;
+            cf val = v[U * R + RegFFT<R>::pos(K)];
+            if (K > 0) val = cmul(val, twiddle<S>(twA, twB, b, K));
+            s[padi(idx<S>(b, K)) * si] = val;
+            fwd_store<S, DIR, U, K + 1>(v, lt, twA, twB, s, si);
+        }
+    }
+    template <int S, int U, int K> static SLMGS_DEVICE void load_elems(cf* v, int lt, const cf* s, int si) {
+        constexpr int R = radix<S>();
+        if constexpr (K < R) {
+            const int b = lt + TPL * U;
+            v[U * R + K] = s[padi(idx<S>(b, K)) * si];
+            load_elems<S, U, K + 1>(v, lt, s, si);
+        }
+    }
+    template <int S, int U, int K>
+    static SLMGS_DEVICE void inv_twiddle(cf* v, int lt, const cf* twA, const cf* twB) {
+        constexpr int R = radix<S>();
+        if constexpr (K < R) {
+            const int b = lt + TPL * U;
+            v[U * R + K] = cmulc(v[U * R + K], twiddle<S>(twA, twB, b, K));
+            inv_twiddle<S, U, K + 1>(v, lt, twA, twB);
+        }
+    }
+    template <int S, int U, int K> static SLMGS_DEVICE void inv_store(cf* v, int lt, cf* s, int si) {
+        constexpr int R = radix<S>();
+        if constexpr (K < R) {
+            const int b = lt + TPL * U;
+            s[padi(idx<S>(b, K)) * si] = v[U * R + RegFFT<R>::pos(K)];
+            inv_store<S, U, K + 1>(v, lt, s, si);
+        }
+    }
+    template <int R, int U, int K> static SLMGS_DEVICE void unscramble(const cf* v, cf* o) {
+        if constexpr (K < R) {
+            o[U * R + K] = v[U * R + RegFFT<R>::pos(K)];
+            unscramble<R, U, K + 1>(v, o);
+        }
+    }
+
+    // ---- forward stage S ------------------------------------------------------------------
+    // S == 0     : v holds the spatial samples (v[u*R0+m] = x[first_index(b_u, m)])
+    // S  > 0     : elements are read from shared memory first
+    // S  < NS-1  : results are twiddled and written back to shared memory (caller barriers)
+    // S == NS-1  : results stay in v, natural order: v[u*R+m] = X[last_index(b_u, m)]
+    template <int S, int U> static SLMGS_DEVICE void fwd_stage_u(cf* v, int lt, const cf* twA, const cf* twB, cf* s,
+                                                                 int si) {
+        constexpr int R = radix<S>();
+        constexpr int Q = E / R;
+        if constexpr (U < Q) {
+            if constexpr (S > 0) load_elems<S, U, 0>(v, lt, s, si);
+            RegFFT<R>::template run<1, 1>(v + U * R);
+            if constexpr (S < NS - 1) fwd_store<S, 1, U, 0>(v, lt, twA, twB, s, si);
+            fwd_stage_u<S, U + 1>(v, lt, twA, twB, s, si);
+        }
+    }
+    template <int S> static SLMGS_DEVICE void fwd_stage(cf* v, int lt, const cf* twA, const cf* twB, cf* s, int si) {
+        fwd_stage_u<S, 0>(v, lt, twA, twB, s, si);
+        if constexpr (S == NS - 1) {
+            cf o[E];
+            unscramble_all<radix<S>(), 0>(v, o);
+            SLMGS_UNROLL
+            for (int i = 0; i < E; ++i) v[i] = o[i];
+        }
+    }
+    template <int R, int U> static SLMGS_DEVICE void unscramble_all(const cf* v, cf* o) {
+        if constexpr (U < E / R) {
+            unscramble<R, U, 0>(v, o);
+            unscramble_all<R, U + 1>(v, o);
+        }
+    }
+
+    // ---- inverse (mirror) stage S -----------------------------------------------------------
+    // S == NS-1 : v holds the spectrum in natural order (v[u*R+m] = X[last_index(b_u, m)])
+    // S  < NS-1 : elements are read from shared memory and multiplied by conj(twiddle_S)
+    // S  > 0    : results are written back to shared memory (caller barriers)
+    // S == 0    : results stay in v, natural order: v[u*R0+m] = x[first_index(b_u, m)] (unnormalised)
+    template <int S, int U> static SLMGS_DEVICE void inv_stage_u(cf* v, int lt, const cf* twA, const cf* twB, cf* s,
+                                                                 int si) {
+        constexpr int R = radix<S>();
+        constexpr int Q = E / R;
+        if constexpr (U < Q) {
+            if constexpr (S < NS - 1) {
+                load_elems<S, U, 0>(v, lt, s, si);
+                inv_twiddle<S, U, 1>(v, lt, twA, twB);
+            }
+            RegFFT<R>::template run<-1, 1>(v + U * R);
+            if constexpr (S > 0) inv_store<S, U, 0>(v, lt, s, si);
+            inv_stage_u<S, U + 1>(v, lt, twA, twB, s, si);
+        }
+    }
+    template <int S> static SLMGS_DEVICE void inv_stage(cf* v, int lt, const cf* twA, const cf* twB, cf* s, int si) {
+        inv_stage_u<S, 0>(v, lt, twA, twB, s, si);
+        if constexpr (S == 0) {
+            cf o[E];
+            unscramble_all<R0, 0>(v, o);
+            SLMGS_UNROLL
+            for (int i = 0; i < E; ++i) v[i] = o[i];
+        }
+    }
+};
+
+}  // namespace slmgs

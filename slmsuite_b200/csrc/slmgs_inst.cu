@@ -1,0 +1,61 @@
+// slmgs_inst.cu -- instantiates the row / column kernels for one line length.
+// Compiled once per size with -DSLMGS_N=<N> (see Makefile) so the sizes build in parallel.
+#include "slmgs_dispatch.h"
+
+#ifndef SLMGS_N
+#error "compile with -DSLMGS_N=<line length>"
+#endif
+
+#define SLMGS_CAT2(a, b) a##b
+#define SLMGS_CAT(a, b) SLMGS_CAT2(a, b)
+
+namespace slmgs {
+
+int SLMGS_CAT(launch_row_, SLMGS_N)(int mode, int gx, int gy, int nthreads, rt_stream s, const RowArgs& a) {
+    switch (mode) {
+        case ROW_FIRST: {
+            typedef RowKernel<SLMGS_N, ROW_FIRST> K;
+            return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
+        }
+        case ROW_FUSED: {
+            typedef RowKernel<SLMGS_N, ROW_FUSED> K;
+            return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
+        }
+        case ROW_LAST: {
+            typedef RowKernel<SLMGS_N, ROW_LAST> K;
+            return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
+        }
+    }
+    return -1;
+}
+
+int SLMGS_CAT(launch_col_, SLMGS_N)(int mode, int gx, int gy, int nthreads, rt_stream s, const ColArgs& a) {
+    switch (mode) {
+        case COL_FWD: {
+            typedef ColKernel<SLMGS_N, COL_FWD> K;
+            return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
+        }
+        case COL_FUSED: {
+            typedef ColKernel<SLMGS_N, COL_FUSED> K;
+            return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
+        }
+        case COL_INV: {
+            typedef ColKernel<SLMGS_N, COL_INV> K;
+            return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
+        }
+    }
+    return -1;
+}
+
+LaunchInfo SLMGS_CAT(launch_info_, SLMGS_N)() {
+    typedef Fft<SLMGS_N> F;
+    LaunchInfo i;
+    i.E = F::E;
+    i.tpl = F::TPL;
+    i.maxt = 16384 / F::E;
+    i.padn = F::PADN;
+    i.ns = F::NS;
+    return i;
+}
+
+}  // namespace slmgs

@@ -1,0 +1,451 @@
+// slmgs_kernels.h -- the two fused kernels of the GS / WGS loop.
+//
+// Index space.  The reference computes farfield = fftshift(fft2(fftshift(nearfield)))
+// (slmsuite/holography/algorithms/_hologram.py:1048) and the inverse with ifftshift (:1070).
+// For even sizes both shifts are the same roll by N/2, so every device array lives in
+// ROLLED index space (stored index = (centred index + N/2) mod N) and the loop is a plain
+// unshifted 2-D DFT; only uploads/downloads roll.  The SLM-sized arrays (phase, amp,
+// propagation kernel) stay in natural (h, w) order; the centred crop of
+// toolbox.unpad (toolbox/__init__.py:1665-1712) is index arithmetic inside the row kernel.
+//
+// One GS/WGS iteration = two kernels over the padded field `fld` (H x W complex64):
+//   ColKernel<H, COL_FUSED>: columns:  forward FFT along y  ->  far-field constraint (+ weight
+//        update, _hologram.py:1550-1653, :1822-1879)  ->  inverse FFT along y
+//   RowKernel<W, ROW_FUSED>: rows:     inverse FFT along x  ->  near-field phase-only projection
+//        (_hologram.py:1026-1036 + :1000-1011)  ->  forward FFT along x
+// Only the h rows that hold the SLM are ever non-zero after the row pass / needed before
+// it, so both kernels touch h*W complex values of `fld`, not H*W.
+#pragma once
+
+#include "slmgs_fft.h"
+#include "slmgs_launch.h"
+
+#include <float.h>
+
+namespace slmgs {
+
+enum { METHOD_GS = 0, METHOD_LEONARDO = 1, METHOD_KIM = 2, METHOD_NOGRETTE = 3, METHOD_WU = 4, METHOD_TANH = 5 };
+enum { ROW_FIRST = 0, ROW_FUSED = 1, ROW_LAST = 2 };
+enum { COL_FWD = 0, COL_FUSED = 1, COL_INV = 2 };
+enum { PHASE_COMPUTE = 0, PHASE_COMPUTE_STORE = 1, PHASE_STORED = 2 };
+
+// ------------------------------------------------------------------------------------------
+// WGS weight multiplier: _hologram.py:1822-1867 (`_update_weights_generic_cupy`), element-wise
+// part.  `famp` is the feedback amplitude, `t` the target amplitude.
+// ------------------------------------------------------------------------------------------
+struct WgsParams {
+    int method;
+    float p;             // feedback_exponent
+    float f;             // feedback_factor
+    float inv_fnorm;     // 1 / ||feedback||_2          (:1830-1831)
+    float neg_inv_mean;  // Nogrette: -(1 / nanmean(fc)) (:1852)
+};
+
+// fc after the normalisation / division / fix-ups, before the method's nonlinearity (:1830-1843)
+SLMGS_HD float wgs_ratio(float famp, float t, const WgsParams& q) {
+    float fc = famp * q.inv_fnorm;
+    if (q.method == METHOD_WU || q.method == METHOD_TANH) {
+        fc = fc * (-q.p);
+        fc = fc + t;
+    } else {
+        fc = fc / t;
+        if (fc == INFINITY) fc = 1.0f;
+        if (t == 0.0f) fc = 1.0f;
+        if (fc != fc) fc = 1.0f;
+    }
+    return fc;
+}
+
+SLMGS_HD float wgs_multiplier(float famp, float t, const WgsParams& q) {
+    float fc = wgs_ratio(famp, t, q);
+    switch (q.method) {
+        case METHOD_LEONARDO:
+        case METHOD_KIM: fc = powf(fc, -q.p); break;  // :1848
+        case METHOD_NOGRETTE:                         // :1851-1855
+            fc = fc * q.neg_inv_mean;
+            fc = fc + 1.0f;
+            fc = fc * (-q.f);
+            fc = fc + 1.0f;
+            fc = 1.0f / fc;
+            break;
+        case METHOD_WU: fc = expf(q.p * fc); break;  // :1857
+        case METHOD_TANH:                            // :1859-1860
+            fc = q.f * tanhf(q.p * fc);
+            fc = fc + 1.0f;
+            break;
+        default: break;
+    }
+    if (fc == INFINITY) fc = 1.0f;  // :1867
+    return fc;
+}
+
+// weights *= fc; nan_to_num(nan=1e-4)  (:1870-1873; +-inf -> +-FLT_MAX as numpy does)
+SLMGS_HD float wgs_apply(float w, float fc) {
+    w = w * fc;
+    if (w != w) return 1.0e-4f;
+    if (w == INFINITY) return FLT_MAX;
+    if (w == -INFINITY) return -FLT_MAX;
+    return w;
+}
+
+// ==========================================================================================
+// Row kernel
+// ==========================================================================================
+struct RowArgs {
+    cf* fld;             // [B][H][W], rolled index space
+    long long fld_bs;    // batch stride (elements)
+    float* phase;        // [B][h][w] near-field phase (natural SLM order)
+    long long phase_bs;
+    const float* amp;    // [h][w] (or [B][h][w]) source amplitude, or nullptr -> amp_scalar
+    long long amp_bs;
+    const float* prop;   // [h][w] propagation kernel or nullptr (shared by the batch)
+    cf* nearfield;       // ROW_LAST only: optional [B][h][w] complex near-field crop (scaled), or nullptr
+    const cf* twA;       // twiddle tables for N = W
+    const cf* twB;
+    float amp_scalar;
+    float scale;         // ROW_LAST near-field scale 1/sqrt(H W)
+    int H, W, h, w, i0, i2;
+    int store_phase;     // ROW_FUSED: also write the phase this iteration
+};
+
+template <int N, int MODE> struct RowKernel {
+    typedef Fft<N> F;
+    typedef RowArgs Args;
+    static constexpr int E = F::E, NS = F::NS;
+    static constexpr int MAXT = 16384 / E;
+    static constexpr int NPHASE = (MODE == ROW_FUSED) ? 2 * NS - 1 : NS;
+    struct State {
+        cf v[E];
+    };
+
+    static size_t smem_bytes(int nthreads) { return NS > 1 ? (size_t)(nthreads / F::TPL) * F::PADN * sizeof(cf) : 0; }
+
+    struct Loc {
+        int lt, sr, fr;  // thread-in-line, SLM row (may be >= h: idle), field row
+        cf* s;           // shared-memory line base
+        long long fbase, pbase;
+        bool active;
+    };
+    static SLMGS_DEVICE Loc locate(const Args& a, cf* smem, const ThreadId& id) {
+        Loc L;
+        const int line = id.tid / F::TPL;
+        const int lines = id.nthreads / F::TPL;
+        L.lt = id.tid % F::TPL;
+        L.sr = id.bx * lines + line;
+        L.active = L.sr < a.h;
+        L.fr = (L.sr + a.i0 + (a.H >> 1)) & (a.H - 1);
+        L.s = smem + (size_t)line * F::PADN;
+        L.fbase = (long long)id.by * a.fld_bs + (long long)L.fr * a.W;
+        L.pbase = (long long)id.by * a.phase_bs + (long long)L.sr * a.w;
+        return L;
+    }
+    // SLM column of rolled x index n, or -1 outside the SLM
+    static SLMGS_DEVICE int slm_col(const Args& a, int n) {
+        const int sc = ((n + (a.W >> 1)) & (a.W - 1)) - a.i2;
+        return (sc >= 0 && sc < a.w) ? sc : -1;
+    }
+    static SLMGS_DEVICE float amp_at(const Args& a, const ThreadId& id, const Loc& L, int sc) {
+        return a.amp ? __ldg(a.amp + (long long)id.by * a.amp_bs + (long long)L.sr * a.w + sc) : a.amp_scalar;
+    }
+
+    // v <- spectrum of this row (inverse input), natural last-stage order
+    static SLMGS_DEVICE void load_spectrum(State& st, const Args& a, const Loc& L) {
+        constexpr int R = F::last_radix();
+        SLMGS_UNROLL
+        for (int u = 0; u < E / R; ++u) {
+            SLMGS_UNROLL
+            for (int m = 0; m < R; ++m) {
+                const int k = F::last_index(L.lt + F::TPL * u, m);
+                st.v[u * R + m] = L.active ? a.fld[L.fbase + k] : cmake(0.f, 0.f);
+            }
+        }
+    }
+    static SLMGS_DEVICE void store_spectrum(State& st, const Args& a, const Loc& L) {
+        constexpr int R = F::last_radix();
+        if (!L.active) return;
+        SLMGS_UNROLL
+        for (int u = 0; u < E / R; ++u) {
+            SLMGS_UNROLL
+            for (int m = 0; m < R; ++m) a.fld[L.fbase + F::last_index(L.lt + F::TPL * u, m)] = st.v[u * R + m];
+        }
+    }
+    // v <- amp * exp(i (phase + prop)) zero-padded: _hologram.py:1000-1011
+    static SLMGS_DEVICE void build_nearfield(State& st, const Args& a, const ThreadId& id, const Loc& L) {
+        constexpr int R = F::R0;
+        SLMGS_UNROLL
+        for (int u = 0; u < E / R; ++u) {
+            SLMGS_UNROLL
+            for (int m = 0; m < R; ++m) {
+                const int n = F::first_index(L.lt + F::TPL * u, m);
+                const int sc = slm_col(a, n);
+                cf val = cmake(0.f, 0.f);
+                if (L.active && sc >= 0) {
+                    float ph = a.phase[L.pbase + sc];
+                    if (a.prop) ph += __ldg(a.prop + (long long)L.sr * a.w + sc);
+                    float sn, cs;
+                    sincosf(ph, &sn, &cs);
+                    const float am = amp_at(a, id, L, sc);
+                    val = cmake(am * cs, am * sn);
+                }
+                st.v[u * R + m] = val;
+            }
+        }
+    }
+    // phase-only projection: _hologram.py:1026-1036 followed by :1000-1011 of the next iteration.
+    // amp * exp(i * arctan2(im, re)) == amp * z / |z|  (z == 0 -> phase 0 -> amp)
+    template <bool REBUILD> static SLMGS_DEVICE void project(State& st, const Args& a, const ThreadId& id, const Loc& L) {
+        constexpr int R = F::R0;
+        SLMGS_UNROLL
+        for (int u = 0; u < E / R; ++u) {
+            SLMGS_UNROLL
+            for (int m = 0; m < R; ++m) {
+                const int n = F::first_index(L.lt + F::TPL * u, m);
+                const int sc = slm_col(a, n);
+                const cf z = st.v[u * R + m];
+                cf val = cmake(0.f, 0.f);
+                if (L.active && sc >= 0) {
+                    if (!REBUILD || a.store_phase) {
+                        float ph = atan2f(z.y, z.x);
+                        if (a.prop) ph -= __ldg(a.prop + (long long)L.sr * a.w + sc);
+                        a.phase[L.pbase + sc] = ph;
+                        if (!REBUILD && a.nearfield)
+                            a.nearfield[(long long)id.by * a.phase_bs + (long long)L.sr * a.w + sc] = cscale(z, a.scale);
+                    }
+                    if (REBUILD) {
+                        const float m2 = z.x * z.x + z.y * z.y;
+                        const float am = amp_at(a, id, L, sc);
+                        if (m2 > 0.f) {
+                            const float r = rsqrtf(m2) * am;
+                            val = cmake(z.x * r, z.y * r);
+                        } else {
+                            val = cmake(am, 0.f);
+                        }
+                    }
+                }
+                st.v[u * R + m] = val;
+            }
+        }
+    }
+
+    template <int P> static SLMGS_DEVICE void phase(State& st, const Args& a, cf* smem, const ThreadId& id) {
+        const Loc L = locate(a, smem, id);
+        if constexpr (MODE == ROW_FIRST) {
+            if constexpr (P == 0) build_nearfield(st, a, id, L);
+            F::template fwd_stage<P>(st.v, L.lt, a.twA, a.twB, L.s, 1);
+            if constexpr (P == NS - 1) store_spectrum(st, a, L);
+        } else if constexpr (MODE == ROW_LAST) {
+            if constexpr (P == 0) load_spectrum(st, a, L);
+            F::template inv_stage<NS - 1 - P>(st.v, L.lt, a.twA, a.twB, L.s, 1);
+            if constexpr (P == NS - 1) project<false>(st, a, id, L);
+        } else {
+            if constexpr (P == 0) load_spectrum(st, a, L);
+            if constexpr (P < NS - 1) {
+                F::template inv_stage<NS - 1 - P>(st.v, L.lt, a.twA, a.twB, L.s, 1);
+            } else if constexpr (P == NS - 1) {
+                F::template inv_stage<0>(st.v, L.lt, a.twA, a.twB, L.s, 1);
+                project<true>(st, a, id, L);
+                F::template fwd_stage<0>(st.v, L.lt, a.twA, a.twB, L.s, 1);
+            } else {
+                F::template fwd_stage<P - (NS - 1)>(st.v, L.lt, a.twA, a.twB, L.s, 1);
+            }
+            if constexpr (P == NPHASE - 1) store_spectrum(st, a, L);
+        }
+    }
+};
+
+// ==========================================================================================
+// Column kernel
+// ==========================================================================================
+struct ColArgs {
+    cf* fld;  // [B][H][W] rolled; only SLM rows are read / written
+    long long fld_bs;
+    const cf* twA;  // twiddle tables for N = H
+    const cf* twB;
+    float* weights;       // [B][H][W] rolled
+    const float* target;  // [B][H][W] rolled (or shared: target_bs == 0)
+    float* phase_ff;      // [B][H][W] rolled
+    float* amp_ff;        // [B][H][W] rolled
+    cf* farfield;         // [B][H][W] rolled, ortho-scaled
+    long long img_bs;     // batch stride of weights / phase_ff / amp_ff / farfield
+    long long target_bs;
+    double* acc;          // [B][acc_bs] accumulators
+    int acc_bs;
+    int w_in_slot;        // accumulator slot holding sum(w^2) of a pending normalisation, or -1
+    int w_out_slot;       // accumulator slot receiving sum(w_new^2), or -1
+    int H, W, h, i0;
+    float scale;          // 1/sqrt(H W): ortho normalisation of the forward transform
+    WgsParams wgs;
+    int wgs_update;       // apply the WGS weight update this iteration (_hologram.py:1552)
+    int phase_mode;       // PHASE_COMPUTE / PHASE_COMPUTE_STORE / PHASE_STORED
+    int mraf;             // target carries NaN noise region (_hologram.py:1495-1548)
+    int mraf_has_factor;
+    float mraf_factor;
+    int store_ampff, store_phaseff, store_farfield;  // COL_FWD outputs
+};
+
+template <int N, int MODE> struct ColKernel {
+    typedef Fft<N> F;
+    typedef ColArgs Args;
+    static constexpr int E = F::E, NS = F::NS;
+    static constexpr int MAXT = 16384 / E;
+    static constexpr int NPHASE = (MODE == COL_FUSED) ? 2 * NS - 1 : NS;
+    struct State {
+        cf v[E];
+    };
+
+    static size_t smem_bytes(int nthreads) { return NS > 1 ? (size_t)(nthreads / F::TPL) * F::PADN * sizeof(cf) : 0; }
+
+    struct Loc {
+        int lt, col, C;  // thread-in-line, column inside the tile, columns per tile
+        int gc;          // global column
+        cf* s;
+        long long fbase, ibase, tbase;
+    };
+    static SLMGS_DEVICE Loc locate(const Args& a, cf* smem, const ThreadId& id) {
+        Loc L;
+        L.C = id.nthreads / F::TPL;
+        L.col = id.tid % L.C;
+        L.lt = id.tid / L.C;
+        L.gc = id.bx * L.C + L.col;
+        L.s = smem + L.col;
+        L.fbase = (long long)id.by * a.fld_bs + L.gc;
+        L.ibase = (long long)id.by * a.img_bs + L.gc;
+        L.tbase = (long long)id.by * a.target_bs + L.gc;
+        return L;
+    }
+    static SLMGS_DEVICE bool slm_row(const Args& a, int n) {
+        const int sr = ((n + (a.H >> 1)) & (a.H - 1)) - a.i0;
+        return sr >= 0 && sr < a.h;
+    }
+
+    static SLMGS_DEVICE void load_rows(State& st, const Args& a, const Loc& L) {
+        constexpr int R = F::R0;
+        SLMGS_UNROLL
+        for (int u = 0; u < E / R; ++u) {
+            SLMGS_UNROLL
+            for (int m = 0; m < R; ++m) {
+                const int n = F::first_index(L.lt + F::TPL * u, m);
+                st.v[u * R + m] = slm_row(a, n) ? a.fld[L.fbase + (long long)n * a.W] : cmake(0.f, 0.f);
+            }
+        }
+    }
+    static SLMGS_DEVICE void store_rows(State& st, const Args& a, const Loc& L) {
+        constexpr int R = F::R0;
+        SLMGS_UNROLL
+        for (int u = 0; u < E / R; ++u) {
+            SLMGS_UNROLL
+            for (int m = 0; m < R; ++m) {
+                const int n = F::first_index(L.lt + F::TPL * u, m);
+                if (slm_row(a, n)) a.fld[L.fbase + (long long)n * a.W] = st.v[u * R + m];
+            }
+        }
+    }
+    static SLMGS_DEVICE void load_farfield(State& st, const Args& a, const Loc& L) {
+        constexpr int R = F::last_radix();
+        SLMGS_UNROLL
+        for (int u = 0; u < E / R; ++u) {
+            SLMGS_UNROLL
+            for (int m = 0; m < R; ++m) {
+                const int k = F::last_index(L.lt + F::TPL * u, m);
+                st.v[u * R + m] = a.farfield[L.ibase + (long long)k * a.W];
+            }
+        }
+    }
+    // COL_FWD epilogue: _hologram.py:951-953 (amp_ff), :934-949 (phase_ff), farfield (ortho-scaled)
+    static SLMGS_DEVICE void store_farfield(State& st, const Args& a, const Loc& L) {
+        constexpr int R = F::last_radix();
+        SLMGS_UNROLL
+        for (int u = 0; u < E / R; ++u) {
+            SLMGS_UNROLL
+            for (int m = 0; m < R; ++m) {
+                const long long off = (long long)F::last_index(L.lt + F::TPL * u, m) * a.W;
+                const cf z = cscale(st.v[u * R + m], a.scale);
+                if (a.store_farfield) a.farfield[L.ibase + off] = z;
+                if (a.store_ampff) a.amp_ff[L.ibase + off] = sqrtf(z.x * z.x + z.y * z.y);
+                if (a.store_phaseff) a.phase_ff[L.ibase + off] = atan2f(z.y, z.x);
+            }
+        }
+    }
+
+    // Far-field constraint (+ fused weight update): _hologram.py:1550-1653.
+    // SCALED: v already carries the ortho scale (COL_INV) or not (COL_FUSED).
+    template <bool SCALED> static SLMGS_DEVICE void constrain(State& st, const Args& a, const ThreadId& id, const Loc& L) {
+        constexpr int R = F::last_radix();
+        double* acc = a.acc + (long long)id.by * a.acc_bs;
+        float win = 1.0f;
+        if (a.w_in_slot >= 0) win = (float)(1.0 / sqrt(acc[a.w_in_slot]));
+        const float fscale = SCALED ? 1.0f : a.scale;
+        double wsum = 0.0;
+        SLMGS_UNROLL
+        for (int u = 0; u < E / R; ++u) {
+            SLMGS_UNROLL
+            for (int m = 0; m < R; ++m) {
+                const long long off = (long long)F::last_index(L.lt + F::TPL * u, m) * a.W;
+                const cf z = st.v[u * R + m];
+                const float m2 = z.x * z.x + z.y * z.y;
+                const float rinv = m2 > 0.f ? rsqrtf(m2) : 0.f;
+                float w = a.weights[L.ibase + off] * win;
+                float t = 1.0f;
+                if (a.wgs_update || a.mraf) t = __ldg(a.target + L.tbase + off);
+                if (a.wgs_update) {
+                    const float famp = m2 * rinv * fscale;  // |F| (ortho-scaled)
+                    w = wgs_apply(w, wgs_multiplier(famp, t, a.wgs));
+                    a.weights[L.ibase + off] = w;
+                    wsum += (double)w * (double)w;
+                }
+                const bool zero_region = a.mraf && t == 0.0f;
+                cf unit;
+                if (a.phase_mode == PHASE_STORED) {
+                    float sn, cs;
+                    sincosf(a.phase_ff[L.ibase + off], &sn, &cs);
+                    unit = cmake(cs, sn);
+                } else {
+                    unit = m2 > 0.f ? cmake(z.x * rinv, z.y * rinv) : cmake(1.0f, 0.f);
+                    if (zero_region) unit = cmake(1.0f, 0.f);  // angle taken after farfield[zero] = 0 (:1613-1622)
+                    if (a.phase_mode == PHASE_COMPUTE_STORE) a.phase_ff[L.ibase + off] = atan2f(unit.y, unit.x);
+                }
+                cf g = cscale(unit, w);
+                if (a.mraf) {
+                    if (zero_region) {
+                        g = cmake(0.f, 0.f);
+                    } else if (t != t) {  // noise region keeps the (scaled) field (:1643-1653)
+                        const float q = a.mraf_has_factor ? fscale * a.mraf_factor : fscale;
+                        g = cscale(z, q);
+                    }
+                }
+                st.v[u * R + m] = g;
+            }
+        }
+        if (a.wgs_update && a.w_out_slot >= 0) accum_add(acc + a.w_out_slot, wsum);
+    }
+
+    template <int P> static SLMGS_DEVICE void phase(State& st, const Args& a, cf* smem, const ThreadId& id) {
+        const Loc L = locate(a, smem, id);
+        if constexpr (MODE == COL_FWD) {
+            if constexpr (P == 0) load_rows(st, a, L);
+            F::template fwd_stage<P>(st.v, L.lt, a.twA, a.twB, L.s, L.C);
+            if constexpr (P == NS - 1) store_farfield(st, a, L);
+        } else if constexpr (MODE == COL_INV) {
+            if constexpr (P == 0) {
+                load_farfield(st, a, L);
+                constrain<true>(st, a, id, L);
+            }
+            F::template inv_stage<NS - 1 - P>(st.v, L.lt, a.twA, a.twB, L.s, L.C);
+            if constexpr (P == NS - 1) store_rows(st, a, L);
+        } else {
+            if constexpr (P == 0) load_rows(st, a, L);
+            if constexpr (P < NS - 1) {
+                F::template fwd_stage<P>(st.v, L.lt, a.twA, a.twB, L.s, L.C);
+            } else if constexpr (P == NS - 1) {
+                F::template fwd_stage<NS - 1>(st.v, L.lt, a.twA, a.twB, L.s, L.C);
+                constrain<false>(st, a, id, L);
+                F::template inv_stage<NS - 1>(st.v, L.lt, a.twA, a.twB, L.s, L.C);
+            } else {
+                F::template inv_stage<2 * NS - 2 - P>(st.v, L.lt, a.twA, a.twB, L.s, L.C);
+            }
+            if constexpr (P == NPHASE - 1) store_rows(st, a, L);
+        }
+    }
+};
+
+}  // namespace slmgs

@@ -1,0 +1,118 @@
+// slmgs_launch.h -- phase-structured kernels: device driver and host-emulation driver.
+//
+// A kernel class K provides
+//     typedef ... Args;            POD argument block (passed by value)
+//     struct State { ... };        per-thread registers that live across barriers
+//     static constexpr int NPHASE; number of barrier-delimited phases
+//     static constexpr int MAXT;   max threads per block (launch bound)
+//     template <int P> static SLMGS_DEVICE void phase(State&, const Args&, cf* smem, const ThreadId&);
+// On the device the phases are chained with __syncthreads() in ONE kernel.  With
+// -DSLMGS_EMULATE (test infrastructure, host compiler) they are executed by loops over
+// (block, phase, thread), which is equivalent because phases only communicate through shared
+// memory across barriers.
+#pragma once
+
+#include "slmgs_common.h"
+
+#ifdef SLMGS_EMULATE
+#include <vector>
+#include <string.h>
+#endif
+
+namespace slmgs {
+
+struct ThreadId {
+    int tid;       // threadIdx.x
+    int nthreads;  // blockDim.x
+    int bx, by;    // blockIdx.x, blockIdx.y
+    int gx;        // gridDim.x
+};
+
+// ---- block-level sum into a global double accumulator ------------------------------------
+#ifndef SLMGS_EMULATE
+SLMGS_DEVICE double warp_sum(double v) {
+    SLMGS_UNROLL
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// Must be called by every thread of the block (full warps).
+SLMGS_DEVICE void accum_add(double* slot, double v) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(slot, v);
+}
+SLMGS_DEVICE void atomic_add_double(double* slot, double v) { atomicAdd(slot, v); }
+SLMGS_DEVICE void atomic_min_float_pos(float* slot, float v) {
+    // valid for non-negative floats (ordered like their bit patterns)
+    atomicMin(reinterpret_cast<int*>(slot), __float_as_int(v));
+}
+#else
+inline void accum_add(double* slot, double v) { *slot += v; }
+inline void atomic_add_double(double* slot, double v) { *slot += v; }
+#endif
+
+#ifndef SLMGS_EMULATE
+template <class K, int P>
+SLMGS_DEVICE void run_phases(typename K::State& st, const typename K::Args& a, cf* smem, const ThreadId& id) {
+    K::template phase<P>(st, a, smem, id);
+    if constexpr (P + 1 < K::NPHASE) {
+        __syncthreads();
+        run_phases<K, P + 1>(st, a, smem, id);
+    }
+}
+
+template <class K> __global__ void __launch_bounds__(K::MAXT, 1) slmgs_kernel(const typename K::Args a) {
+    extern __shared__ __align__(16) unsigned char slmgs_smem_raw[];
+    cf* smem = reinterpret_cast<cf*>(slmgs_smem_raw);
+    typename K::State st;
+    ThreadId id;
+    id.tid = threadIdx.x;
+    id.nthreads = blockDim.x;
+    id.bx = blockIdx.x;
+    id.by = blockIdx.y;
+    id.gx = gridDim.x;
+    run_phases<K, 0>(st, a, smem, id);
+}
+
+// returns cudaError_t as int
+template <class K>
+int launch_kernel(int gx, int gy, int nthreads, size_t smem_bytes, cudaStream_t stream, const typename K::Args& a) {
+    static bool attr_set[64] = {false};  // per instantiation, per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(slmgs_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_set[dev & 63] = true;
+    }
+    slmgs_kernel<K><<<dim3(gx, gy, 1), dim3(nthreads, 1, 1), smem_bytes, stream>>>(a);
+    return (int)cudaGetLastError();
+}
+#else
+template <class K, int P>
+inline void emu_phases(std::vector<typename K::State>& st, const typename K::Args& a, cf* smem, ThreadId id) {
+    for (int t = 0; t < id.nthreads; ++t) {
+        id.tid = t;
+        K::template phase<P>(st[t], a, smem, id);
+    }
+    if constexpr (P + 1 < K::NPHASE) emu_phases<K, P + 1>(st, a, smem, id);
+}
+
+template <class K>
+int launch_kernel(int gx, int gy, int nthreads, size_t smem_bytes, void* /*stream*/, const typename K::Args& a) {
+    std::vector<typename K::State> st(nthreads);
+    std::vector<cf> smem(smem_bytes / sizeof(cf) + 2);
+    for (int by = 0; by < gy; ++by)
+        for (int bx = 0; bx < gx; ++bx) {
+            ThreadId id;
+            id.tid = 0;
+            id.nthreads = nthreads;
+            id.bx = bx;
+            id.by = by;
+            id.gx = gx;
+            emu_phases<K, 0>(st, a, smem.data(), id);
+        }
+    return 0;
+}
+#endif
+
+}  // namespace slmgs

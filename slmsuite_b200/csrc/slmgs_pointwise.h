@@ -1,0 +1,266 @@
+// slmgs_pointwise.h -- element-wise / reduction kernels used by the stepped (callback, stats,
+// Nogrette, MRAF+WGS, spot-feedback) path and by uploads/downloads.  Same phase structure as
+// the FFT kernels so the host emulation covers them too.
+#pragma once
+
+#include "slmgs_kernels.h"
+
+namespace slmgs {
+
+enum {
+    EW_ROLL_F32 = 0,    // dst[roll(y,x)] = src[y,x]
+    EW_ROLL_C64 = 1,
+    EW_SUMSQ = 2,       // acc[slot0] += nansum(src^2)
+    EW_RATIO_SUM = 3,   // acc[slot0] += sum(wgs_ratio(src=amp_ff, target))           (Nogrette mean)
+    EW_WGS_UPDATE = 4,  // dst=weights <- wgs_apply(...); acc[slot1] += sum(w^2)
+    EW_SCALE = 5,       // dst *= 1/sqrt(acc[slot0])
+    EW_STATS1 = 6,      // acc[slot0..2] += sum f^2, nansum t^2, nansum t f           (_stats.py:51-76)
+    EW_FILL_NAN0 = 7,   // dst = nan_to_num(src, nan=0)                                (reset_weights, :608-614)
+    EW_ABS_C64 = 8,     // dst(f32) = |src(c64)|
+};
+
+struct ElemArgs {
+    const void* src;
+    void* dst;
+    const float* target;
+    double* acc;  // [B][acc_bs]
+    long long n;  // elements per hologram
+    long long src_bs, dst_bs, target_bs;
+    int acc_bs;
+    int H, W;  // EW_ROLL_*
+    int slot0, slot1, slot2;
+    WgsParams wgs;
+    int fnorm_slot;  // EW_WGS_UPDATE / EW_RATIO_SUM: inv_fnorm = 1/sqrt(acc[fnorm_slot]) if >= 0
+    int mean_slot;   // EW_WGS_UPDATE: Nogrette mean = acc[mean_slot] / n
+};
+
+template <int OP> struct ElemKernel {
+    typedef ElemArgs Args;
+    static constexpr int MAXT = 256;
+    static constexpr int NPHASE = 1;
+    struct State {};
+
+    template <int P> static SLMGS_DEVICE void phase(State&, const Args& a, cf*, const ThreadId& id) {
+        double* acc = a.acc ? a.acc + (long long)id.by * a.acc_bs : nullptr;
+        const float* srcf = reinterpret_cast<const float*>(a.src) + (long long)id.by * a.src_bs;
+        const cf* srcc = reinterpret_cast<const cf*>(a.src) + (long long)id.by * a.src_bs;
+        float* dstf = reinterpret_cast<float*>(a.dst) + (long long)id.by * a.dst_bs;
+        cf* dstc = reinterpret_cast<cf*>(a.dst) + (long long)id.by * a.dst_bs;
+        const float* tgt = a.target ? a.target + (long long)id.by * a.target_bs : nullptr;
+        WgsParams q = a.wgs;
+        if (OP == EW_WGS_UPDATE || OP == EW_RATIO_SUM) {
+            if (a.fnorm_slot >= 0) q.inv_fnorm = (float)(1.0 / sqrt(acc[a.fnorm_slot]));
+            if (OP == EW_WGS_UPDATE && a.mean_slot >= 0) q.neg_inv_mean = -(1.0f / (float)(acc[a.mean_slot] / (double)a.n));
+        }
+        float sc = 1.0f;
+        if (OP == EW_SCALE) sc = (float)(1.0 / sqrt(acc[a.slot0]));
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        const long long stride = (long long)id.gx * id.nthreads;
+        for (long long i = (long long)id.bx * id.nthreads + id.tid; i < a.n; i += stride) {
+            if (OP == EW_ROLL_F32 || OP == EW_ROLL_C64) {
+                const int y = (int)(i / a.W), x = (int)(i % a.W);
+                const long long j = (long long)((y + (a.H >> 1)) % a.H) * a.W + ((x + (a.W >> 1)) % a.W);
+                if (OP == EW_ROLL_F32) dstf[j] = srcf[i];
+                else dstc[j] = srcc[i];
+            } else if (OP == EW_SUMSQ) {
+                const float v = srcf[i];
+                if (v == v) s0 += (double)v * (double)v;
+            } else if (OP == EW_RATIO_SUM) {
+                s0 += (double)wgs_ratio(srcf[i], tgt[i], q);
+            } else if (OP == EW_WGS_UPDATE) {
+                const float w = wgs_apply(dstf[i], wgs_multiplier(srcf[i], tgt[i], q));
+                dstf[i] = w;
+                s1 += (double)w * (double)w;
+            } else if (OP == EW_SCALE) {
+                dstf[i] *= sc;
+            } else if (OP == EW_STATS1) {
+                const float f = srcf[i], t = tgt[i];
+                s0 += (double)f * (double)f;
+                if (t == t) {
+                    s1 += (double)t * (double)t;
+                    s2 += (double)t * (double)f;
+                }
+            } else if (OP == EW_FILL_NAN0) {
+                const float v = srcf[i];
+                dstf[i] = (v == v) ? v : 0.0f;
+            } else if (OP == EW_ABS_C64) {
+                const cf z = srcc[i];
+                dstf[i] = sqrtf(z.x * z.x + z.y * z.y);
+            }
+        }
+        if (OP == EW_SUMSQ || OP == EW_RATIO_SUM) accum_add(acc + a.slot0, s0);
+        if (OP == EW_WGS_UPDATE) accum_add(acc + a.slot1, s1);
+        if (OP == EW_STATS1) {
+            accum_add(acc + a.slot0, s0);
+            accum_add(acc + a.slot1, s1);
+            accum_add(acc + a.slot2, s2);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Second statistics pass (_stats.py:78-101): over pixels with target power != 0 and not NaN,
+//   ratio = (f^2/fsum)/(t^2/tsum) -> min, max;  err = t^2/tsum - f^2/fsum -> min, max, sum, sum^2, count
+// One partial record of 8 doubles per block; the host finishes the reduction.
+// ------------------------------------------------------------------------------------------
+struct Stats2Args {
+    const float* f;
+    const float* t;
+    double* partial;  // [B][gx][8]
+    const double* acc;
+    long long n, f_bs, t_bs;
+    int acc_bs, fsum_slot, tsum_slot;
+};
+
+struct Stats2Kernel {
+    typedef Stats2Args Args;
+    static constexpr int MAXT = 256;
+    static constexpr int NPHASE = 2;
+    struct State {};
+
+    template <int P> static SLMGS_DEVICE void phase(State&, const Args& a, cf* smem, const ThreadId& id) {
+        double* sm = reinterpret_cast<double*>(smem);  // [nthreads][8]
+        if (P == 0) {
+            const double* acc = a.acc + (long long)id.by * a.acc_bs;
+            const double fi = 1.0 / acc[a.fsum_slot], ti = 1.0 / acc[a.tsum_slot];
+            const float* f = a.f + (long long)id.by * a.f_bs;
+            const float* t = a.t + (long long)id.by * a.t_bs;
+            double rmin = INFINITY, rmax = -INFINITY, emin = INFINITY, emax = -INFINITY, es = 0, es2 = 0, cnt = 0;
+            const long long stride = (long long)id.gx * id.nthreads;
+            for (long long i = (long long)id.bx * id.nthreads + id.tid; i < a.n; i += stride) {
+                const float tv = t[i];
+                const double tp = (double)tv * (double)tv * ti;
+                if (tv == tv && tp != 0.0) {
+                    const double fp = (double)f[i] * (double)f[i] * fi;
+                    const double r = fp / tp, e = tp - fp;
+                    rmin = r < rmin ? r : rmin;
+                    rmax = r > rmax ? r : rmax;
+                    emin = e < emin ? e : emin;
+                    emax = e > emax ? e : emax;
+                    es += e;
+                    es2 += e * e;
+                    cnt += 1;
+                }
+            }
+            double* o = sm + (size_t)id.tid * 8;
+            o[0] = rmin; o[1] = rmax; o[2] = emin; o[3] = emax; o[4] = es; o[5] = es2; o[6] = cnt; o[7] = 0;
+        } else if (id.tid == 0) {
+            double r[8] = {INFINITY, -INFINITY, INFINITY, -INFINITY, 0, 0, 0, 0};
+            for (int t = 0; t < id.nthreads; ++t) {
+                const double* o = sm + (size_t)t * 8;
+                r[0] = o[0] < r[0] ? o[0] : r[0];
+                r[1] = o[1] > r[1] ? o[1] : r[1];
+                r[2] = o[2] < r[2] ? o[2] : r[2];
+                r[3] = o[3] > r[3] ? o[3] : r[3];
+                r[4] += o[4]; r[5] += o[5]; r[6] += o[6];
+            }
+            double* out = a.partial + ((long long)id.by * id.gx + id.bx) * 8;
+            for (int k = 0; k < 8; ++k) out[k] = r[k];
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Spot feedback (SpotHologram._update_weights, _spots.py:1573-1624 + analysis.take,
+// analysis/__init__.py:61-204 with centered=True, integrate=True, clip=False).
+//   gather : pw[n] = sum over the w x w window round (x_n, y_n) of img^2, float64 accumulation,
+//            offsets floor(arange(w) - (w-1)/2), negative indices wrap (NumPy semantics).
+//            Coordinates are in the reference's centred convention; the image is rolled.
+//   update : N-vector WGS update against spot_amp, normalised over the N spots, scattered back.
+// ------------------------------------------------------------------------------------------
+struct SpotArgs {
+    const float* img;     // amp_ff [B][H][W] rolled
+    float* weights;       // [B][H][W] rolled
+    const int* sx;        // [N] integer spot x (centred convention)
+    const int* sy;
+    const float* spot_amp;  // [N] target amplitudes (host float64 in the reference, rounded once here)
+    double* pw;           // [B][N] window powers (output of gather, input of update)
+    long long img_bs;
+    int H, W, N, width;
+    WgsParams wgs;
+};
+
+struct SpotGatherKernel {
+    typedef SpotArgs Args;
+    static constexpr int MAXT = 256;
+    static constexpr int NPHASE = 1;
+    struct State {};
+    template <int P> static SLMGS_DEVICE void phase(State&, const Args& a, cf*, const ThreadId& id) {
+        const float* img = a.img + (long long)id.by * a.img_bs;
+        for (int n = id.bx * id.nthreads + id.tid; n < a.N; n += id.gx * id.nthreads) {
+            // floor(k - (w-1)/2): for odd w this is k - (w-1)/2, for even w it is k - w/2
+            const int base = (a.width & 1) ? -((a.width - 1) / 2) : -(a.width / 2);
+            double s = 0.0;
+            for (int dy = 0; dy < a.width; ++dy) {
+                int y = a.sy[n] + base + dy;
+                if (y < 0) y += a.H;  // NumPy negative-index wrap
+                const int ry = (y + (a.H >> 1)) % a.H;
+                for (int dx = 0; dx < a.width; ++dx) {
+                    int x = a.sx[n] + base + dx;
+                    if (x < 0) x += a.W;
+                    const int rx = (x + (a.W >> 1)) % a.W;
+                    const float v = img[(long long)ry * a.W + rx];
+                    s += (double)(v * v);  // reference squares in float32, sums in float64
+                }
+            }
+            a.pw[(long long)id.by * a.N + n] = s;
+        }
+    }
+};
+
+// single block per hologram
+struct SpotUpdateKernel {
+    typedef SpotArgs Args;
+    static constexpr int MAXT = 1024;
+    static constexpr int NPHASE = 7;
+    struct State {};
+
+    static SLMGS_DEVICE long long pix(const Args& a, int n) {
+        const int ry = (a.sy[n] + (a.H >> 1)) % a.H, rx = (a.sx[n] + (a.W >> 1)) % a.W;
+        return (long long)ry * a.W + rx;
+    }
+    // smem doubles: [0..nthreads) scratch, then [nthreads + k] block scalars
+    template <int P> static SLMGS_DEVICE void phase(State&, const Args& a, cf* smem, const ThreadId& id) {
+        double* sm = reinterpret_cast<double*>(smem);
+        double* scal = sm + id.nthreads;  // 0: sum f^2, 1: sum ratio, 2: sum w^2
+        const double* pw = a.pw + (long long)id.by * a.N;
+        float* wts = a.weights + (long long)id.by * a.img_bs;
+        WgsParams q = a.wgs;
+        if (P == 0) {  // partial sum of feedback^2 (feedback = float32(sqrt(pw)))
+            double s = 0.0;
+            for (int n = id.tid; n < a.N; n += id.nthreads) {
+                const float f = (float)sqrt(pw[n]);
+                if (f == f) s += (double)f * (double)f;
+            }
+            sm[id.tid] = s;
+        } else if (P == 1 || P == 3 || P == 5) {
+            if (id.tid == 0) {
+                double s = 0.0;
+                for (int t = 0; t < id.nthreads; ++t) s += sm[t];
+                scal[P >> 1] = s;
+            }
+        } else if (P == 2) {  // Nogrette mean of the ratio
+            q.inv_fnorm = (float)(1.0 / sqrt(scal[0]));
+            double s = 0.0;
+            if (q.method == METHOD_NOGRETTE)
+                for (int n = id.tid; n < a.N; n += id.nthreads) s += (double)wgs_ratio((float)sqrt(pw[n]), a.spot_amp[n], q);
+            sm[id.tid] = s;
+        } else if (P == 4) {  // update, partial sum of w^2
+            q.inv_fnorm = (float)(1.0 / sqrt(scal[0]));
+            q.neg_inv_mean = -(1.0f / (float)(scal[1] / (double)a.N));
+            double s = 0.0;
+            for (int n = id.tid; n < a.N; n += id.nthreads) {
+                const long long p = pix(a, n);
+                const float w = wgs_apply(wts[p], wgs_multiplier((float)sqrt(pw[n]), a.spot_amp[n], q));
+                wts[p] = w;
+                s += (double)w * (double)w;
+            }
+            sm[id.tid] = s;
+        } else if (P == 6) {  // normalise over the N spots (:1877 on the N-vector)
+            const float sc = (float)(1.0 / sqrt(scal[2]));
+            for (int n = id.tid; n < a.N; n += id.nthreads) wts[pix(a, n)] *= sc;
+        }
+    }
+};
+
+}  // namespace slmgs

@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""
+bench.py -- GS iterations/sec at 4096^2 complex64 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path on the host cores
+
+Workload (BASELINE.json configs[1]): Hologram, SLM 1152x1920 zero-padded to 4096x4096, 64-spot
+target, method "WGS-Kim", 50 iterations per optimize().  One STEP = one optimize() of 50 iterations
+from a reset state (first row pass + 50 fused iterations + _populate_results).  N > 1: every rank
+runs its own independent hologram (weak scaling, no collective inside the loop) and the run ends with
+ONE all-gather of the final phases.
+
+Timing: CUDA events on the library's own stream (slmgs_timer_*), barrier + synchronise on both
+sides, max over ranks.  The per-iteration working set (fld rows 38 MB + weights/target/phase_ff 192 MB)
+exceeds the 126 MB L2, so no explicit flush is needed between iterations.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "GS iterations/sec @ 4096^2 c64"
+SHAPE = (4096, 4096)
+SLM_SHAPE = (1152, 1920)
+METHOD = "WGS-Kim"
+ITERS = 50
+N_SPOTS = 64
+WORKLOAD = "Hologram 1920x1152 SLM padded to 4096x4096, WGS-Kim, 50 iters (BASELINE configs[1])"
+
+
+def make_inputs(seed):
+    """64 unit spots at default_rng(1) positions, seeded explicit phase."""
+    rng = np.random.default_rng(1)
+    pts = rng.integers(0, SHAPE[0], (2, N_SPOTS))
+    target = np.zeros(SHAPE, dtype=np.float32)
+    target[pts[1], pts[0]] = 1
+    phase = np.random.default_rng(1000 + seed).uniform(-np.pi, np.pi, SLM_SHAPE).astype(np.float32)
+    return target, phase
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.05] or [r for (_, r) in self.rows]
+        for r in rows:
+            p = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(p[0]))
+                smax = float(p[1])
+            except Exception:
+                continue
+            for name, val in zip(names, p[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithm (oracle port of the NumPy path) on the host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, iters = args
+    from oracle import gs_oracle
+
+    target, phase = make_inputs(seed)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        h = gs_oracle.OracleHologram(target, phase=phase, slm_shape=SLM_SHAPE)
+        t0 = time.perf_counter()
+        h.optimize(method=METHOD, maxiter=iters, verbose=False)
+        return time.perf_counter() - t0
+
+
+def cpu_it_per_s(procs, iters):
+    """`procs` independent holograms, one per process (NumPy's pocketfft and ufuncs are single-threaded)."""
+    if procs == 1:
+        dt = _cpu_worker((0, iters))
+        return iters / dt, dt
+    import multiprocessing as mp
+
+    with mp.get_context("spawn").Pool(procs) as pool:
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(i, iters) for i in range(procs)])
+        dt = time.perf_counter() - t0
+    return procs * iters / dt, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 32))
+    iters = 2  # bounded sample: 2 WGS-Kim iterations (+ the trailing _populate_results transform) per hologram
+    vals = []
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_it_per_s(procs, 1)
+    t_all = time.perf_counter()
+    for _ in range(max(1, args.steps)):
+        v, _dt = cpu_it_per_s(procs, iters)
+        vals.append(v)
+        if time.perf_counter() - t_all > 150:
+            break
+    value = float(np.median(vals))
+    sample = (f"{procs} independent holograms in {procs} processes (NumPy is single-threaded), {iters} {METHOD} "
+              f"iterations each at 4096^2 incl. the trailing _populate_results transform; median of {len(vals)} step(s)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "it/s", "n_gpus": args.gpus,
+        "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * procs * iters / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "method": METHOD, "shape": list(SHAPE), "slm_shape": list(SLM_SHAPE)},
+        "cpu_baseline": {"value": value, "unit": "it/s", "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo
+# ------------------------------------------------------------------------------------------------
+def run_b200(args, rank, local_rank, world):
+    import torch  # plumbing only: pinned host memory, torch.distributed, NCCL all-gather
+
+    from slmsuite_b200 import Hologram, _lib
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    lib = _lib.use_library(_lib.DEFAULT_LIBRARY)
+    target, phase0 = make_inputs(rank)
+    holo = Hologram(target, phase=phase0, slm_shape=SLM_SHAPE, device=local_rank)
+    ctx = holo._ctx
+    chk = holo._check
+    chk(lib.slmgs_save_phase(ctx))
+
+    def step_resident():
+        """inputs already in HBM: restore phase + weights on the device, then one optimize()."""
+        chk(lib.slmgs_restore_phase(ctx))
+        holo.reset(reset_phase=False)
+        holo.flags["fixed_phase"] = False
+        holo.optimize(METHOD, maxiter=ITERS, verbose=False)
+
+    # pinned host buffers for the end-to-end path
+    pin_target = torch.from_numpy(np.ascontiguousarray(holo.target)).pin_memory()
+    pin_phase = torch.from_numpy(phase0).pin_memory()
+    pin_out = torch.empty(SLM_SHAPE, dtype=torch.float32).pin_memory()
+    fp = C.POINTER(C.c_float)
+    p_target = C.cast(pin_target.data_ptr(), fp)
+    p_phase = C.cast(pin_phase.data_ptr(), fp)
+    p_out = C.cast(pin_out.data_ptr(), fp)
+
+    def step_e2e():
+        """through the C ABI with HOST buffers: upload target + phase, optimize, download the phase."""
+        chk(lib.slmgs_set_target(ctx, p_target, 0))
+        chk(lib.slmgs_set_phase(ctx, p_phase))
+        holo.reset(reset_phase=False)
+        holo.flags["fixed_phase"] = False
+        holo.optimize(METHOD, maxiter=ITERS, verbose=False)
+        chk(lib.slmgs_get_phase(ctx, p_out))
+
+    def barrier():
+        chk(lib.slmgs_sync(ctx))
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # the final all-gather of phases (one per job), over the library's device buffer
+    class _DevPhase:
+        def __init__(self):
+            self.__cuda_array_interface__ = {
+                "shape": SLM_SHAPE, "typestr": "<f4", "data": (lib.slmgs_phase_device_ptr(ctx), False), "version": 3}
+
+    def allgather_phases():
+        if dist is None:
+            return 0.0
+        src = torch.as_tensor(_DevPhase(), device=torch.device("cuda", local_rank))
+        out = torch.empty((world,) + SLM_SHAPE, dtype=torch.float32, device=src.device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_gather_into_tensor(out, src)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    # ---- warm-up ------------------------------------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    step_e2e()
+    allgather_phases()
+    barrier()
+
+    # ---- timed region: K steps, device events on the launching stream ---------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    chk(lib.slmgs_profile_enable(ctx, 1))
+    launches0 = lib.slmgs_launch_count(ctx)
+    barrier()
+    w0 = time.perf_counter()
+    chk(lib.slmgs_timer_start(ctx))
+    for _ in range(args.steps):
+        step_resident()
+    ms = C.c_float()
+    chk(lib.slmgs_timer_stop(ctx, C.byref(ms)))
+    ag_ms = allgather_phases()
+    barrier()
+    w1 = time.perf_counter()
+    launches = lib.slmgs_launch_count(ctx) - launches0
+    prof_ms = (C.c_float * 6)()
+    prof_n = (C.c_int * 6)()
+    chk(lib.slmgs_profile_read(ctx, prof_ms, prof_n))
+    chk(lib.slmgs_profile_enable(ctx, 0))
+    clocks = sampler.stop(w0, w1)
+    total_ms = max_over_ranks(float(ms.value) + ag_ms)
+    wall_ms = max_over_ranks(1e3 * (w1 - w0))
+    total_launches = int(sum_over_ranks(float(launches)))
+
+    # ---- end-to-end: same steps through host buffers ---------------------------------------------
+    barrier()
+    chk(lib.slmgs_timer_start(ctx))
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    chk(lib.slmgs_sync(ctx))
+    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - e0))  # host clock: the H2D/D2H copies are synchronous calls
+    ms2 = C.c_float()
+    chk(lib.slmgs_timer_stop(ctx, C.byref(ms2)))
+    barrier()
+
+    iters_total = world * args.steps * ITERS
+    value = iters_total / (total_ms * 1e-3)
+    e2e_value = iters_total / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (column fused) -------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    P = SHAPE[0] * SHAPE[1]
+    hW = SLM_SHAPE[0] * SHAPE[1]
+    # model bytes per launch (DESIGN.md "Algorithmic bytes"): column kernel = forward + inverse column pass
+    # (4 x 8P) + weights 4P + target 4P + weights write 4P (WGS) [+ phase_ff 4P once Kim has fixed the phase];
+    # averaged over the 50 iterations of this workload: 1 GS-like, 9 WGS, 40 Kim-fixed.
+    col_model = (1 * 36 + 9 * 44 + 40 * 48) / 50.0 * P
+    row_model = 32.0 * P
+    # bytes the implementation must actually move (zero-padding skipped: only the h SLM rows of fld are touched)
+    col_actual = 16.0 * hW + (1 * 4 + 9 * 12 + 40 * 16) / 50.0 * P
+    row_actual = 16.0 * hW
+    kern = {}
+    names = ["row_first", "row_fused", "row_last", "col_forward", "col_fused", "col_inverse"]
+    for k in range(6):
+        if prof_n[k]:
+            kern[names[k]] = {"launches": int(prof_n[k]), "avg_ms": float(prof_ms[k]) / int(prof_n[k])}
+    share = {k: v["avg_ms"] * v["launches"] for k, v in kern.items()}
+    tot = sum(share.values()) or 1.0
+    dom = "col_fused" if share.get("col_fused", 0) >= share.get("row_fused", 0) else "row_fused"
+    dom_ms = kern[dom]["avg_ms"]
+    model = col_model if dom == "col_fused" else row_model
+    actual = col_actual if dom == "col_fused" else row_actual
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+    except Exception:
+        pass
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": model / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+        "frac": model / (dom_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+        "model_bytes_per_launch": model, "avg_launch_ms": dom_ms,
+        "actual_bytes_per_launch": actual, "actual_gbs": actual / (dom_ms * 1e-3) / 1e9,
+        "actual_frac": actual / (dom_ms * 1e-3) / 1e9 / peak,
+        "kernel_share_of_step": {k: v / tot for k, v in share.items()},
+        "kernels": kern,
+        "iteration_model_frac": (76.0 * 9 + 80.0 * 40 + 68.0) / 50.0 * P * (value / world) / 1e9 / peak,
+    }
+
+    # ---- CPU baseline (oracle port of the reference's NumPy path), bounded sample ------------------
+    cpu_iters = 2
+    cpu_value, cpu_dt = cpu_it_per_s(1, cpu_iters)
+    cpu = {"value": cpu_value, "unit": "it/s", "cores": 1, "kind": "port",
+           "sample": f"{cpu_iters} {METHOD} iterations at 4096^2 (+ trailing _populate_results transform), oracle port, "
+                     f"1 process ({os.cpu_count()} host cores present), {cpu_dt:.1f} s"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "it/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "c64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "method": METHOD, "iters_per_step": ITERS, "shape": list(SHAPE),
+                   "slm_shape": list(SLM_SHAPE), "n_spots": N_SPOTS, "parallelism": f"replicas x{world}",
+                   "l2": "working set 230 MB/iteration > 126 MB L2, no flush needed",
+                   "final_allgather_ms": ag_ms},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "it/s", "h2d_bytes_per_step": int(4 * P + 4 * SLM_SHAPE[0] * SLM_SHAPE[1]),
+                "d2h_bytes_per_step": int(4 * SLM_SHAPE[0] * SLM_SHAPE[1]), "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": total_launches,
+        "wall_ms_per_step": wall_ms / args.steps,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -172,13 +172,13 @@ static void make_twiddles(int n, std::vector<cf>& a, std::vector<cf>& b) {
     int r0, r1, r2;
     switch (n) {
         case 16: r0 = 16; r1 = 1; r2 = 1; break;
-        case 32: r0 = 16; r1 = 2; r2 = 1; break;
-        case 64: r0 = 16; r1 = 4; r2 = 1; break;
-        case 128: r0 = 16; r1 = 8; r2 = 1; break;
+        case 32: r0 = 2; r1 = 16; r2 = 1; break;
+        case 64: r0 = 4; r1 = 16; r2 = 1; break;
+        case 128: r0 = 8; r1 = 16; r2 = 1; break;
         case 256: r0 = 16; r1 = 16; r2 = 1; break;
-        case 512: r0 = 16; r1 = 16; r2 = 2; break;
-        case 1024: r0 = 16; r1 = 16; r2 = 4; break;
-        case 2048: r0 = 16; r1 = 16; r2 = 8; break;
+        case 512: r0 = 2; r1 = 16; r2 = 16; break;
+        case 1024: r0 = 4; r1 = 16; r2 = 16; break;
+        case 2048: r0 = 8; r1 = 16; r2 = 16; break;
         case 4096: r0 = 16; r1 = 16; r2 = 16; break;
         default: r0 = 32; r1 = 16; r2 = 16; break;
     }
@@ -662,6 +662,14 @@ extern "C" int slmgs_run(slmgs_ctx* c, const slmgs_params* params, int n_iter, i
             if (ca.wgs_update) {
                 ca.w_out_slot = (c->w_pending == ACC_W0) ? ACC_W1 : ACC_W0;
                 if ((e = zero_slot(c, ca.w_out_slot))) return e;
+            }
+            if (ca.phase_mode == PHASE_COMPUTE_STORE) {
+                // the iteration that fixes the far-field phase (WGS-Kim): keep angle(farfield) with one extra
+                // forward column pass, then constrain against the stored phase
+                ColArgs fa = col_args(c);
+                fa.store_phaseff = 1;
+                if ((e = run_col(c, COL_FWD, fa))) return e;
+                ca.phase_mode = PHASE_STORED;
             }
             if ((e = run_col(c, COL_FUSED, ca))) return e;
             if (ca.wgs_update) c->w_pending = ca.w_out_slot;

@@ -34,26 +34,23 @@
 namespace slmgs {
 
 template <int N> struct Plan;
-#define SLMGS_PLAN(N_, E_, A_, B_, C_)                                          \
+// E: points per thread; R0,R1,R2: stage radices (smallest first so the two big stages keep 16 consecutive
+// lanes on consecutive addresses); P2: pad of the k0 stride (see "Shared memory layout" below).
+#define SLMGS_PLAN(N_, E_, A_, B_, C_, P2_)                                     \
     template <> struct Plan<N_> {                                               \
-        static constexpr int E = E_, R0 = A_, R1 = B_, R2 = C_;                 \
+        static constexpr int E = E_, R0 = A_, R1 = B_, R2 = C_, P2 = P2_;       \
     };
-SLMGS_PLAN(16, 16, 16, 1, 1)
-SLMGS_PLAN(32, 16, 16, 2, 1)
-SLMGS_PLAN(64, 16, 16, 4, 1)
-SLMGS_PLAN(128, 16, 16, 8, 1)
-SLMGS_PLAN(256, 16, 16, 16, 1)
-SLMGS_PLAN(512, 16, 16, 16, 2)
-SLMGS_PLAN(1024, 16, 16, 16, 4)
-SLMGS_PLAN(2048, 16, 16, 16, 8)
-SLMGS_PLAN(4096, 16, 16, 16, 16)
-SLMGS_PLAN(8192, 32, 32, 16, 16)
+SLMGS_PLAN(16, 16, 16, 1, 1, 0)
+SLMGS_PLAN(32, 16, 2, 16, 1, 1)
+SLMGS_PLAN(64, 16, 4, 16, 1, 1)
+SLMGS_PLAN(128, 16, 8, 16, 1, 1)
+SLMGS_PLAN(256, 16, 16, 16, 1, 1)
+SLMGS_PLAN(512, 16, 2, 16, 16, 8)
+SLMGS_PLAN(1024, 16, 4, 16, 16, 4)
+SLMGS_PLAN(2048, 16, 8, 16, 16, 2)
+SLMGS_PLAN(4096, 16, 16, 16, 16, 1)
+SLMGS_PLAN(8192, 32, 32, 16, 16, 1)
 #undef SLMGS_PLAN
-
-// Padded shared-memory index: one pad element per 16 and one more per 256.  Makes the three
-// access patterns (consecutive, stride R2, stride M1) hit distinct 8-byte bank pairs within
-// each half-warp for the plans above (DESIGN.md "Shared memory layout").
-SLMGS_HD int padi(int i) { return i + (i >> 4) + (i >> 8); }
 
 template <int N> struct Fft {
     typedef Plan<N> P;
@@ -61,18 +58,29 @@ template <int N> struct Fft {
     static constexpr int NS = 1 + (R1 > 1) + (R2 > 1);
     static constexpr int M1 = R1 * R2;
     static constexpr int TPL = N / E;
-    static constexpr int PADN = N + (N >> 4) + (N >> 8) + 1;
     static_assert(R0 * R1 * R2 == N, "bad plan");
+    // Shared memory layout.  A line index i = k0*M1 + x*R2 + y (k0 < R0, x < R1, y < R2) is stored at
+    //     k0*T2 + x*T1 + y,   T1 = R2 + (R2 > 1),   T2 = R1*T1 + P2
+    // i.e. plain digit strides with small pads.  Element m of a butterfly is then always at
+    // base(b) + m*const, so the 16 shared-memory accesses of a stage use one address register with
+    // compile-time offsets.  Pads are chosen so that within every half-warp (16 lanes, 8-byte accesses)
+    // the three access patterns hit 16 distinct bank pairs:
+    //   lanes along y (stages A, B): consecutive;    lanes along k0 (stage C): stride T2 = P2 (mod 16),
+    //   P2*k0 + k1 distinct for the R0 x 16/R0 lanes of a half-warp.
+    static constexpr int T1 = R2 + (R2 > 1 ? 1 : 0);
+    static constexpr int T2 = R1 * T1 + P::P2;
+    static constexpr int PADN = R0 * T2 + 1;
 
     template <int S> static constexpr int radix() { return S == 0 ? R0 : S == 1 ? R1 : R2; }
     static constexpr int last_radix() { return radix<NS - 1>(); }
 
-    // line index of element m of butterfly b at stage S
-    template <int S> static SLMGS_HD int idx(int b, int m) {
-        if (S == 0) return m * M1 + b;
-        if (S == 1) return (b / R2) * M1 + m * R2 + (b % R2);
-        return (b % R0) * M1 + (b / R0) * R2 + m;
+    // shared-memory position of element 0 of butterfly b at stage S, and the stride between elements
+    template <int S> static SLMGS_HD int sbase(int b) {
+        if (S == 0) return (b / R2) * T1 + (b % R2);
+        if (S == 1) return (b / R2) * T2 + (b % R2);
+        return (b % R0) * T2 + (b / R0) * T1;
     }
+    template <int S> static constexpr int sstride() { return S == 0 ? T2 : S == 1 ? T1 : 1; }
     // twiddle applied after forward stage S (S < NS-1) to output m of butterfly b
     template <int S> static SLMGS_DEVICE cf twiddle(const cf* SLMGS_RESTRICT twA, const cf* SLMGS_RESTRICT twB, int b,
                                                    int m) {
@@ -91,7 +99,7 @@ template <int N> struct Fft {
             const int b = lt + TPL * U;
             cf val = v[U * R + RegFFT<R>::pos(K)];
             if (K > 0) val = cmul(val, twiddle<S>(twA, twB, b, K));
-            s[padi(idx<S>(b, K)) * si] = val;
+            s[(sbase<S>(b) + K * sstride<S>()) * si] = val;
             fwd_store<S, DIR, U, K + 1>(v, lt, twA, twB, s, si);
         }
     }
@@ -99,7 +107,7 @@ template <int N> struct Fft {
         constexpr int R = radix<S>();
         if constexpr (K < R) {
             const int b = lt + TPL * U;
-            v[U * R + K] = s[padi(idx<S>(b, K)) * si];
+            v[U * R + K] = s[(sbase<S>(b) + K * sstride<S>()) * si];
             load_elems<S, U, K + 1>(v, lt, s, si);
         }
     }
@@ -116,7 +124,7 @@ template <int N> struct Fft {
         constexpr int R = radix<S>();
         if constexpr (K < R) {
             const int b = lt + TPL * U;
-            s[padi(idx<S>(b, K)) * si] = v[U * R + RegFFT<R>::pos(K)];
+            s[(sbase<S>(b) + K * sstride<S>()) * si] = v[U * R + RegFFT<R>::pos(K)];
             inv_store<S, U, K + 1>(v, lt, s, si);
         }
     }

@@ -83,8 +83,8 @@ static int launch_row(int n, int mode, int gx, int gy, int nt, rt_stream s, cons
 #undef X
     return -1;
 }
-static int launch_col(int n, int mode, int gx, int gy, int nt, rt_stream s, const ColArgs& a) {
-#define X(N_) if (n == N_) return launch_col_##N_(mode, gx, gy, nt, s, a);
+static int launch_col(int n, int mode, int var, int gx, int gy, int nt, rt_stream s, const ColArgs& a) {
+#define X(N_) if (n == N_) return launch_col_##N_(mode, var, gx, gy, nt, s, a);
     SLMGS_FOR_SIZES(X)
 #undef X
     return -1;
@@ -209,7 +209,9 @@ static void choose_geometry(slmgs_ctx* c) {
     {
         const LaunchInfo& li = c->irow;
         int lo = li.tpl < 32 ? 32 : li.tpl;
-        int nt = li.maxt;
+        // two resident blocks per SM (<= 512 threads, <= ~70 KB shared memory each) overlap one block's
+        // global-memory phases with the other's butterflies: measured 108 vs 124 us at 4096^2 on B200
+        int nt = li.maxt > 512 && li.tpl <= 512 ? 512 : li.maxt;
         while (nt > lo) {
             const int lines = nt / li.tpl;
             const long long blocks = (long long)((c->h + lines - 1) / lines) * c->B;
@@ -374,6 +376,8 @@ static ElemArgs elem_args(slmgs_ctx* c, const void* src, void* dst, long long n)
     a.target = c->target;
     a.acc = c->acc; a.acc_bs = ACC_N;
     a.H = c->H; a.W = c->W;
+    a.C = c->col_threads / c->icol.tpl;
+    a.unroll = 0;
     a.fnorm_slot = -1; a.mean_slot = -1;
     return a;
 }
@@ -406,6 +410,7 @@ static int upload_rolled(slmgs_ctx* c, const float* host, float* dst, int batch)
 static int download_rolled(slmgs_ctx* c, const float* src, float* host, int batch) {
     const long long P = (long long)c->H * c->W;
     ElemArgs a = elem_args(c, src, c->stage_f, P);
+    a.unroll = 1;
     int e = launch_elem<EW_ROLL_F32>(c, a, batch);  // roll by N/2 is an involution for even N
     if (e) return e;
     RT(c, rt_d2h(host, c->stage_f, (size_t)batch * P * sizeof(float), c->stream));
@@ -608,7 +613,15 @@ static int run_row(slmgs_ctx* c, int mode, const RowArgs& a) {
 static int run_col(slmgs_ctx* c, int mode, const ColArgs& a) {
     c->launches++;
     prof_mark(c, 3 + mode, true);
-    int e = rt_check(c, launch_col(c->H, mode, c->col_gx, c->B, c->col_threads, c->stream, a), "column kernel launch");
+    // compile-time specialisation of the fused constraint (slmgs_kernels.h, VAR_*)
+    int var = VAR_GENERAL;
+    if (mode == COL_FUSED && !a.mraf) {
+        const bool pow_like = a.wgs.method == METHOD_LEONARDO || a.wgs.method == METHOD_KIM;
+        if (!a.wgs_update && a.phase_mode == PHASE_COMPUTE) var = VAR_GS;
+        else if (a.wgs_update && pow_like && a.phase_mode == PHASE_COMPUTE) var = VAR_POW;
+        else if (a.wgs_update && pow_like && a.phase_mode == PHASE_STORED) var = VAR_POW_STORED;
+    }
+    int e = rt_check(c, launch_col(c->H, mode, var, c->col_gx, c->B, c->col_threads, c->stream, a), "column kernel launch");
     prof_mark(c, 3 + mode, false);
     return e;
 }
@@ -728,6 +741,7 @@ extern "C" int slmgs_get_farfield(slmgs_ctx* c, float* out) {
     const long long P = (long long)c->H * c->W;
     if (!c->stage_c && (e = dev_alloc(c, &c->stage_c, (size_t)c->B * P))) return e;
     ElemArgs a = elem_args(c, c->farfield, c->stage_c, P);
+    a.unroll = 1;
     if ((e = launch_elem<EW_ROLL_C64>(c, a, c->B))) return e;
     RT(c, rt_d2h(out, c->stage_c, (size_t)c->B * P * sizeof(cf), c->stream));
     return SLMGS_OK;
@@ -786,6 +800,7 @@ static SpotArgs spot_args(slmgs_ctx* c, int width) {
     memset(&a, 0, sizeof a);
     a.img = c->amp_ff; a.weights = c->weights; a.sx = c->spot_x; a.sy = c->spot_y; a.spot_amp = c->spot_amp;
     a.pw = c->spot_pw; a.img_bs = (long long)c->H * c->W; a.H = c->H; a.W = c->W; a.N = c->n_spots; a.width = width;
+    a.C = c->col_threads / c->icol.tpl;
     return a;
 }
 

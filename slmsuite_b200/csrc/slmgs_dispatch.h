@@ -20,7 +20,7 @@ struct LaunchInfo {
 
 #define SLMGS_DECL(N_)                                                                                        \
     int launch_row_##N_(int mode, int gx, int gy, int nthreads, rt_stream s, const RowArgs& a);               \
-    int launch_col_##N_(int mode, int gx, int gy, int nthreads, rt_stream s, const ColArgs& a);               \
+    int launch_col_##N_(int mode, int var, int gx, int gy, int nthreads, rt_stream s, const ColArgs& a);               \
     LaunchInfo launch_info_##N_();
 SLMGS_DECL(16)
 SLMGS_DECL(32)

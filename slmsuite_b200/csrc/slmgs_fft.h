@@ -48,7 +48,10 @@ SLMGS_PLAN(256, 16, 16, 16, 1, 1)
 SLMGS_PLAN(512, 16, 2, 16, 16, 8)
 SLMGS_PLAN(1024, 16, 4, 16, 16, 4)
 SLMGS_PLAN(2048, 16, 8, 16, 16, 2)
-SLMGS_PLAN(4096, 16, 16, 16, 16, 1)
+#ifndef SLMGS_E4096
+#define SLMGS_E4096 16
+#endif
+SLMGS_PLAN(4096, SLMGS_E4096, 16, 16, 16, 1)
 SLMGS_PLAN(8192, 32, 32, 16, 16, 1)
 #undef SLMGS_PLAN
 

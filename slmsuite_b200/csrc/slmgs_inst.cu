@@ -29,16 +29,24 @@ int SLMGS_CAT(launch_row_, SLMGS_N)(int mode, int gx, int gy, int nthreads, rt_s
     return -1;
 }
 
-int SLMGS_CAT(launch_col_, SLMGS_N)(int mode, int gx, int gy, int nthreads, rt_stream s, const ColArgs& a) {
+template <int VAR> static int launch_col_fused(int gx, int gy, int nthreads, rt_stream s, const ColArgs& a) {
+    typedef ColKernel<SLMGS_N, COL_FUSED, VAR> K;
+    return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
+}
+
+int SLMGS_CAT(launch_col_, SLMGS_N)(int mode, int var, int gx, int gy, int nthreads, rt_stream s, const ColArgs& a) {
     switch (mode) {
         case COL_FWD: {
             typedef ColKernel<SLMGS_N, COL_FWD> K;
             return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
         }
-        case COL_FUSED: {
-            typedef ColKernel<SLMGS_N, COL_FUSED> K;
-            return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
-        }
+        case COL_FUSED:
+            switch (var) {
+                case VAR_GS: return launch_col_fused<VAR_GS>(gx, gy, nthreads, s, a);
+                case VAR_POW: return launch_col_fused<VAR_POW>(gx, gy, nthreads, s, a);
+                case VAR_POW_STORED: return launch_col_fused<VAR_POW_STORED>(gx, gy, nthreads, s, a);
+                default: return launch_col_fused<VAR_GENERAL>(gx, gy, nthreads, s, a);
+            }
         case COL_INV: {
             typedef ColKernel<SLMGS_N, COL_INV> K;
             return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);

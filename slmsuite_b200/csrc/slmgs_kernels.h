@@ -28,6 +28,7 @@ enum { METHOD_GS = 0, METHOD_LEONARDO = 1, METHOD_KIM = 2, METHOD_NOGRETTE = 3, 
 enum { ROW_FIRST = 0, ROW_FUSED = 1, ROW_LAST = 2 };
 enum { COL_FWD = 0, COL_FUSED = 1, COL_INV = 2 };
 enum { PHASE_COMPUTE = 0, PHASE_COMPUTE_STORE = 1, PHASE_STORED = 2 };
+enum { VAR_GENERAL = 0, VAR_GS = 1, VAR_POW = 2, VAR_POW_STORED = 3 };
 
 // ------------------------------------------------------------------------------------------
 // WGS weight multiplier: _hologram.py:1822-1867 (`_update_weights_generic_cupy`), element-wise
@@ -69,6 +70,7 @@ SLMGS_DEVICE float fast_tanh(float x) {
 }
 SLMGS_DEVICE void fast_sincos(float x, float* s, float* c) { __sincosf(x, s, c); }
 #else
+inline float __fdividef(float a, float b) { return a / b; }
 inline float fast_pow(float x, float y) { return powf(x, y); }
 inline float fast_exp(float x) { return expf(x); }
 inline float fast_tanh(float x) { return tanhf(x); }
@@ -98,7 +100,16 @@ SLMGS_HD float wgs_multiplier(float famp, float t, const WgsParams& q) {
     return fc;
 }
 
+// Leonardo / Kim: (F/||F|| / T)^-p with the reference's fix-ups (inf, T == 0, nan -> 1 before the power,
+// inf -> 1 after) folded into one select.
+SLMGS_DEVICE float wgs_multiplier_pow_fast(float famp, float t, const WgsParams& q) {
+    float fc = __fdividef(famp * q.inv_fnorm, t);
+    fc = fast_pow(fc, -q.p);
+    return (t == 0.0f || !(fc < INFINITY)) ? 1.0f : fc;
+}
+
 SLMGS_DEVICE float wgs_multiplier_fast(float famp, float t, const WgsParams& q) {
+    if (q.method == METHOD_LEONARDO || q.method == METHOD_KIM) return wgs_multiplier_pow_fast(famp, t, q);
     float fc = wgs_ratio(famp, t, q);
     switch (q.method) {
         case METHOD_LEONARDO:
@@ -298,6 +309,16 @@ template <int N, int MODE> struct RowKernel {
 // ==========================================================================================
 // Column kernel
 // ==========================================================================================
+// Layout of the far-field-shaped images (target, weights, phase_ff, amp_ff, farfield): the column
+// kernel of a context always works on tiles of C adjacent columns, so these private device buffers
+// are stored tile-major, [W/C tiles][H rows][C columns] in rolled coordinates: a tile is one
+// contiguous block and a warp's access (8 rows x 4 columns, or 2 x 16, ...) is one fully used
+// 128-byte line instead of 8 half-used sectors.  Only uploads/downloads and the spot gather need
+// the mapping; element-wise kernels are layout agnostic.
+SLMGS_HD long long image_index(int ry, int rx, int H, int C) {
+    return (long long)(rx / C) * H * C + (long long)ry * C + (rx % C);
+}
+
 struct ColArgs {
     cf* fld;  // [B][H][W] rolled; only SLM rows are read / written
     long long fld_bs;
@@ -325,7 +346,7 @@ struct ColArgs {
     int store_ampff, store_phaseff, store_farfield;  // COL_FWD outputs
 };
 
-template <int N, int MODE> struct ColKernel {
+template <int N, int MODE, int VAR = 0> struct ColKernel {
     typedef Fft<N> F;
     typedef ColArgs Args;
     static constexpr int E = F::E, NS = F::NS;
@@ -351,8 +372,9 @@ template <int N, int MODE> struct ColKernel {
         L.gc = id.bx * L.C + L.col;
         L.s = smem + L.col;
         L.fbase = (long long)id.by * a.fld_bs + L.gc;
-        L.ibase = (long long)id.by * a.img_bs + L.gc;
-        L.tbase = (long long)id.by * a.target_bs + L.gc;
+        // far-field-shaped images are tile-major: [W/C tiles][H rows][C columns] (image_index below)
+        L.ibase = (long long)id.by * a.img_bs + (long long)id.bx * a.H * L.C + L.col;
+        L.tbase = (long long)id.by * a.target_bs + (long long)id.bx * a.H * L.C + L.col;
         return L;
     }
     static SLMGS_DEVICE bool slm_row(const Args& a, int n) {
@@ -389,7 +411,7 @@ template <int N, int MODE> struct ColKernel {
             SLMGS_UNROLL
             for (int m = 0; m < R; ++m) {
                 const int k = F::last_index(L.lt + F::TPL * u, m);
-                st.v[u * R + m] = a.farfield[L.ibase + (long long)k * a.W];
+                st.v[u * R + m] = a.farfield[L.ibase + (long long)k * L.C];
             }
         }
     }
@@ -400,7 +422,7 @@ template <int N, int MODE> struct ColKernel {
         for (int u = 0; u < E / R; ++u) {
             SLMGS_UNROLL
             for (int m = 0; m < R; ++m) {
-                const long long off = (long long)F::last_index(L.lt + F::TPL * u, m) * a.W;
+                const long long off = (long long)F::last_index(L.lt + F::TPL * u, m) * L.C;
                 const cf z = cscale(st.v[u * R + m], a.scale);
                 if (a.store_farfield) a.farfield[L.ibase + off] = z;
                 if (a.store_ampff) a.amp_ff[L.ibase + off] = sqrtf(z.x * z.x + z.y * z.y);
@@ -410,37 +432,62 @@ template <int N, int MODE> struct ColKernel {
     }
 
     // Far-field constraint (+ fused weight update): _hologram.py:1550-1653.
-    // SCALED: v already carries the ortho scale (COL_INV) or not (COL_FUSED).
+    // SCALED: v already carries the ortho scale (COL_INV, accurate math) or not (COL_FUSED, fast math).
+    // VAR specialises the fused kernel at compile time (fewer branches, fewer live registers):
+    //   VAR_GENERAL everything decided at run time; VAR_GS no update, phase from the field, no MRAF;
+    //   VAR_POW Leonardo/Kim update, phase from the field; VAR_POW_STORED the same with the stored phase.
+    // The loads of weights / target / phase_ff are software pipelined two elements ahead of their use:
+    // the weights store of element i may alias later loads as far as the compiler knows, so without
+    // the explicit prefetch every element would pay a full memory round trip.
     template <bool SCALED> static SLMGS_DEVICE void constrain(State& st, const Args& a, const ThreadId& id, const Loc& L) {
         constexpr int R = F::last_radix();
+        constexpr bool GEN = SCALED || VAR == VAR_GENERAL;
+        const bool update = GEN ? (a.wgs_update != 0) : (VAR == VAR_POW || VAR == VAR_POW_STORED);
+        const bool stored = GEN ? (a.phase_mode == PHASE_STORED) : (VAR == VAR_POW_STORED);
+        const bool mraf = GEN ? (a.mraf != 0) : false;
+        const bool need_t = update || mraf;
         double* acc = a.acc + (long long)id.by * a.acc_bs;
         float win = 1.0f;
         if (a.w_in_slot >= 0) win = (float)(1.0 / sqrt(acc[a.w_in_slot]));
         const float fscale = SCALED ? 1.0f : a.scale;
-        double wsum = 0.0;
+        float wsum = 0.0f;
+        const float* SLMGS_RESTRICT wp = a.weights + L.ibase;
+        const float* SLMGS_RESTRICT tp = a.target + L.tbase;
+        const float* SLMGS_RESTRICT pp = a.phase_ff + L.ibase;
+        float wq[E], tq[E], pq[E];
+        constexpr int AHEAD = 2;
         SLMGS_UNROLL
-        for (int u = 0; u < E / R; ++u) {
-            SLMGS_UNROLL
-            for (int m = 0; m < R; ++m) {
-                const long long off = (long long)F::last_index(L.lt + F::TPL * u, m) * a.W;
-                const cf z = st.v[u * R + m];
+        for (int e = 0; e < E + AHEAD; ++e) {
+            if (e < E) {  // issue the loads of element e
+                const int off = F::last_index(L.lt + F::TPL * (e / R), e % R) * L.C;
+                wq[e] = wp[off];
+                tq[e] = need_t ? __ldg(tp + off) : 1.0f;
+                pq[e] = stored ? __ldg(pp + off) : 0.0f;
+            }
+            if (e >= AHEAD) {  // consume element i
+                const int i = e - AHEAD;
+                const int off = F::last_index(L.lt + F::TPL * (i / R), i % R) * L.C;
+                const cf z = st.v[i];
                 const float m2 = z.x * z.x + z.y * z.y;
                 const float rinv = m2 > 0.f ? rsqrtf(m2) : 0.f;
-                float w = a.weights[L.ibase + off] * win;
-                float t = 1.0f;
-                if (a.wgs_update || a.mraf) t = __ldg(a.target + L.tbase + off);
-                if (a.wgs_update) {
+                float w = wq[i] * win;
+                const float t = tq[i];
+                if (update) {
                     const float famp = m2 * rinv * fscale;  // |F| (ortho-scaled)
-                    w = wgs_apply(w, SCALED ? wgs_multiplier(famp, t, a.wgs) : wgs_multiplier_fast(famp, t, a.wgs));
+                    float fc;
+                    if (SCALED) fc = wgs_multiplier(famp, t, a.wgs);
+                    else if (VAR == VAR_POW || VAR == VAR_POW_STORED) fc = wgs_multiplier_pow_fast(famp, t, a.wgs);
+                    else fc = wgs_multiplier_fast(famp, t, a.wgs);
+                    w = wgs_apply(w, fc);
                     a.weights[L.ibase + off] = w;
-                    wsum += (double)w * (double)w;
+                    wsum += w * w;
                 }
-                const bool zero_region = a.mraf && t == 0.0f;
+                const bool zero_region = mraf && t == 0.0f;
                 cf unit;
-                if (a.phase_mode == PHASE_STORED) {
+                if (stored) {
                     float sn, cs;
-                    if (SCALED) sincosf(a.phase_ff[L.ibase + off], &sn, &cs);
-                    else fast_sincos(a.phase_ff[L.ibase + off], &sn, &cs);
+                    if (SCALED) sincosf(pq[i], &sn, &cs);
+                    else fast_sincos(pq[i], &sn, &cs);
                     unit = cmake(cs, sn);
                 } else {
                     unit = m2 > 0.f ? cmake(z.x * rinv, z.y * rinv) : cmake(1.0f, 0.f);
@@ -449,7 +496,7 @@ template <int N, int MODE> struct ColKernel {
                     if (SCALED && a.phase_mode == PHASE_COMPUTE_STORE) a.phase_ff[L.ibase + off] = atan2f(unit.y, unit.x);
                 }
                 cf g = cscale(unit, w);
-                if (a.mraf) {
+                if (mraf) {
                     if (zero_region) {
                         g = cmake(0.f, 0.f);
                     } else if (t != t) {  // noise region keeps the (scaled) field (:1643-1653)
@@ -457,10 +504,10 @@ template <int N, int MODE> struct ColKernel {
                         g = cscale(z, q);
                     }
                 }
-                st.v[u * R + m] = g;
+                st.v[i] = g;
             }
         }
-        if (a.wgs_update && a.w_out_slot >= 0) accum_add(acc + a.w_out_slot, wsum);
+        if (update && a.w_out_slot >= 0) accum_add(acc + a.w_out_slot, (double)wsum);
     }
 
     template <int P> static SLMGS_DEVICE void phase(State& st, const Args& a, cf* smem, const ThreadId& id) {

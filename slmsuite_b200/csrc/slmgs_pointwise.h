@@ -8,8 +8,8 @@
 namespace slmgs {
 
 enum {
-    EW_ROLL_F32 = 0,    // dst[roll(y,x)] = src[y,x]
-    EW_ROLL_C64 = 1,
+    EW_ROLL_F32 = 0,    // upload: dst[image_index(roll(y,x))] = src[y,x]   (centred row-major -> rolled tile-major)
+    EW_ROLL_C64 = 1,    // download (a.unroll): dst[y,x] = src[image_index(roll(y,x))]
     EW_SUMSQ = 2,       // acc[slot0] += nansum(src^2)
     EW_RATIO_SUM = 3,   // acc[slot0] += sum(wgs_ratio(src=amp_ff, target))           (Nogrette mean)
     EW_WGS_UPDATE = 4,  // dst=weights <- wgs_apply(...); acc[slot1] += sum(w^2)
@@ -28,6 +28,8 @@ struct ElemArgs {
     long long src_bs, dst_bs, target_bs;
     int acc_bs;
     int H, W;  // EW_ROLL_*
+    int C;     // EW_ROLL_*: column-tile width of the device image layout
+    int unroll;  // EW_ROLL_*: 0 = upload (host layout -> device layout), 1 = download
     int slot0, slot1, slot2;
     WgsParams wgs;
     int fnorm_slot;  // EW_WGS_UPDATE / EW_RATIO_SUM: inv_fnorm = 1/sqrt(acc[fnorm_slot]) if >= 0
@@ -59,9 +61,14 @@ template <int OP> struct ElemKernel {
         for (long long i = (long long)id.bx * id.nthreads + id.tid; i < a.n; i += stride) {
             if (OP == EW_ROLL_F32 || OP == EW_ROLL_C64) {
                 const int y = (int)(i / a.W), x = (int)(i % a.W);
-                const long long j = (long long)((y + (a.H >> 1)) % a.H) * a.W + ((x + (a.W >> 1)) % a.W);
-                if (OP == EW_ROLL_F32) dstf[j] = srcf[i];
-                else dstc[j] = srcc[i];
+                const long long j = image_index((y + (a.H >> 1)) % a.H, (x + (a.W >> 1)) % a.W, a.H, a.C);
+                if (OP == EW_ROLL_F32) {
+                    if (a.unroll) dstf[i] = srcf[j];
+                    else dstf[j] = srcf[i];
+                } else {
+                    if (a.unroll) dstc[i] = srcc[j];
+                    else dstc[j] = srcc[i];
+                }
             } else if (OP == EW_SUMSQ) {
                 const float v = srcf[i];
                 if (v == v) s0 += (double)v * (double)v;
@@ -177,6 +184,7 @@ struct SpotArgs {
     double* pw;           // [B][N] window powers (output of gather, input of update)
     long long img_bs;
     int H, W, N, width;
+    int C;  // column-tile width of the image layout
     WgsParams wgs;
 };
 
@@ -199,7 +207,7 @@ struct SpotGatherKernel {
                     int x = a.sx[n] + base + dx;
                     if (x < 0) x += a.W;
                     const int rx = (x + (a.W >> 1)) % a.W;
-                    const float v = img[(long long)ry * a.W + rx];
+                    const float v = img[image_index(ry, rx, a.H, a.C)];
                     s += (double)(v * v);  // reference squares in float32, sums in float64
                 }
             }
@@ -217,7 +225,7 @@ struct SpotUpdateKernel {
 
     static SLMGS_DEVICE long long pix(const Args& a, int n) {
         const int ry = (a.sy[n] + (a.H >> 1)) % a.H, rx = (a.sx[n] + (a.W >> 1)) % a.W;
-        return (long long)ry * a.W + rx;
+        return image_index(ry, rx, a.H, a.C);
     }
     // smem doubles: [0..nthreads) scratch, then [nthreads + k] block scalars
     template <int P> static SLMGS_DEVICE void phase(State&, const Args& a, cf* smem, const ThreadId& id) {

@@ -218,8 +218,12 @@ class Hologram:
         except Exception:
             pass
 
+    def _bshape(self, shape):
+        """Array shape of a per-hologram quantity (HologramBatch prepends the batch axis)."""
+        return tuple(shape)
+
     def _download(self, fn, shape, dtype=np.float32):
-        out = np.empty(shape, dtype=dtype)
+        out = np.empty(self._bshape(shape), dtype=dtype)
         self._check(fn(self._ctx, out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
 

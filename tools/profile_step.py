@@ -19,9 +19,10 @@ ap.add_argument("--slm", type=int, nargs=2, default=None)
 ap.add_argument("--iters", type=int, default=12)
 ap.add_argument("--dense", action="store_true", help="dense random target instead of 64 spots")
 ap.add_argument("--fix", type=int, default=4, help="fix_phase_iteration for WGS-Kim")
+ap.add_argument("--lib", default=None, help="alternative build of libslmgs.so")
 a = ap.parse_args()
 
-_lib.use_library(_lib.DEFAULT_LIBRARY)
+_lib.use_library(a.lib or _lib.DEFAULT_LIBRARY)
 shape = (a.shape, a.shape)
 slm = tuple(a.slm) if a.slm else shape
 rng = np.random.default_rng(1)

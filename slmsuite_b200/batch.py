@@ -107,6 +107,7 @@ class HologramBatch(Hologram):
             self.reset_weights()
 
     def _upload_target(self):
+        self._mraf_cache = None
         self._check(self._lib.slmgs_set_target(self._ctx, _lib.fptr(_lib.f32(self._target)),
                                                1 if self._shared_target else 0))
 
@@ -143,10 +144,6 @@ class HologramBatch(Hologram):
     @property
     def nearfield(self):
         raise NotImplementedError("nearfield is rebuilt per hologram: use Hologram for that accessor")
-
-    def _mraf_enabled(self):
-        with np.errstate(all="ignore"):
-            return bool(np.isnan(np.sum(self._target)))
 
     def _iteration_params(self, mraf, stepped):
         if self.flags.get("fix_phase_efficiency", None) is not None:

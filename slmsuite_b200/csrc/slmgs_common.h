@@ -36,6 +36,24 @@ namespace slmgs {
 
 typedef float2 cf;  // complex float, (re, im)
 
+// Streaming global loads: the field and the far-field images are touched once per kernel, so they
+// must not evict the twiddle tables from L1 (ld.global.L1::no_allocate).
+#if defined(__CUDACC__) && !defined(SLMGS_EMULATE)
+SLMGS_DEVICE float ld_stream(const float* p) {
+    float v;
+    asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+SLMGS_DEVICE float2 ld_stream(const float2* p) {
+    float2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+#else
+inline float ld_stream(const float* p) { return *p; }
+inline float2 ld_stream(const float2* p) { return *p; }
+#endif
+
 SLMGS_HD cf cmake(float re, float im) { return make_float2(re, im); }
 SLMGS_HD cf cadd(cf a, cf b) { return make_float2(a.x + b.x, a.y + b.y); }
 SLMGS_HD cf csub(cf a, cf b) { return make_float2(a.x - b.x, a.y - b.y); }

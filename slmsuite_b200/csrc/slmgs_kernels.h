@@ -209,7 +209,7 @@ template <int N, int MODE> struct RowKernel {
             SLMGS_UNROLL
             for (int m = 0; m < R; ++m) {
                 const int k = F::last_index(L.lt + F::TPL * u, m);
-                st.v[u * R + m] = L.active ? a.fld[L.fbase + k] : cmake(0.f, 0.f);
+                st.v[u * R + m] = L.active ? ld_stream(a.fld + L.fbase + k) : cmake(0.f, 0.f);
             }
         }
     }
@@ -389,7 +389,7 @@ template <int N, int MODE, int VAR = 0> struct ColKernel {
             SLMGS_UNROLL
             for (int m = 0; m < R; ++m) {
                 const int n = F::first_index(L.lt + F::TPL * u, m);
-                st.v[u * R + m] = slm_row(a, n) ? a.fld[L.fbase + (long long)n * a.W] : cmake(0.f, 0.f);
+                st.v[u * R + m] = slm_row(a, n) ? ld_stream(a.fld + L.fbase + (long long)n * a.W) : cmake(0.f, 0.f);
             }
         }
     }
@@ -411,7 +411,7 @@ template <int N, int MODE, int VAR = 0> struct ColKernel {
             SLMGS_UNROLL
             for (int m = 0; m < R; ++m) {
                 const int k = F::last_index(L.lt + F::TPL * u, m);
-                st.v[u * R + m] = a.farfield[L.ibase + (long long)k * L.C];
+                st.v[u * R + m] = ld_stream(a.farfield + L.ibase + (long long)k * L.C);
             }
         }
     }
@@ -460,9 +460,9 @@ template <int N, int MODE, int VAR = 0> struct ColKernel {
         for (int e = 0; e < E + AHEAD; ++e) {
             if (e < E) {  // issue the loads of element e
                 const int off = F::last_index(L.lt + F::TPL * (e / R), e % R) * L.C;
-                wq[e] = wp[off];
-                tq[e] = need_t ? __ldg(tp + off) : 1.0f;
-                pq[e] = stored ? __ldg(pp + off) : 0.0f;
+                wq[e] = ld_stream(wp + off);
+                tq[e] = need_t ? ld_stream(tp + off) : 1.0f;
+                pq[e] = stored ? ld_stream(pp + off) : 0.0f;
             }
             if (e >= AHEAD) {  // consume element i
                 const int i = e - AHEAD;

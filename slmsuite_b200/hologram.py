@@ -197,6 +197,7 @@ class Hologram:
 
         self.flags = kwargs
         self._target = None
+        self._mraf_cache = None
         self._set_target(target, reset_weights=False)
 
         self._phase_set = False
@@ -315,6 +316,7 @@ class Hologram:
             self.reset_weights()
 
     def _upload_target(self):
+        self._mraf_cache = None
         self._check(self._lib.slmgs_set_target(self._ctx, _lib.fptr(_lib.f32(self._target)), 0))
 
     def set_target(self, new_target, reset_weights=False):
@@ -476,9 +478,12 @@ class Hologram:
             print("", end="", flush=True)
 
     def _mraf_enabled(self):
-        """_hologram.py:1495-1501."""
-        with np.errstate(all="ignore"):
-            return bool(np.isnan(np.sum(self._target)))
+        """_hologram.py:1495-1501 (``isnan(sum(target))``), evaluated once per target: the reference sums the
+        full target on every optimize() call, which costs milliseconds on the host at 4096^2."""
+        if self._mraf_cache is None:
+            with np.errstate(all="ignore"):
+                self._mraf_cache = bool(np.isnan(np.sum(self._target)))
+        return self._mraf_cache
 
     def _fusable(self, callback):
         """

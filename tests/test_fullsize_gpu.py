@@ -1,0 +1,147 @@
+"""Full-size checks on the B200 (BASELINE.json sizes): side-by-side parity with the oracle for a few
+iterations, and size-independent properties of the loop where the oracle would take minutes."""
+import warnings
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_rmse(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def _spots(shape, n, seed):
+    rng = np.random.default_rng(seed)
+    pts = rng.integers(0, shape[0], (2, n))
+    t = np.zeros(shape, dtype=np.float32)
+    t[pts[1], pts[0]] = 1
+    return t
+
+
+def test_config2_three_iterations_vs_oracle(cuda):
+    """BASELINE configs[1] (1152x1920 in 4096^2, WGS-Kim) for 3 iterations against the oracle; 1e-5 rel-RMSE."""
+    from oracle import gs_oracle
+    from slmsuite_b200 import Hologram
+
+    shape, slm = (4096, 4096), (1152, 1920)
+    target = _spots(shape, 64, 1)
+    phase = np.random.default_rng(2).uniform(-np.pi, np.pi, slm).astype(np.float32)
+    kw = dict(method="WGS-Kim", maxiter=3, verbose=False, fix_phase_iteration=2)
+    a = Hologram(target, phase=phase, slm_shape=slm)
+    a.optimize(**kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        b = gs_oracle.OracleHologram(target, phase=phase, slm_shape=slm)
+        b.optimize(**kw)
+    assert rel_rmse(a.amp_ff, b.amp_ff) <= 1e-5
+    assert rel_rmse(a.weights, b.weights) <= 1e-5
+    assert a.flags["fixed_phase"] == b.flags["fixed_phase"] is True
+    dphi = np.angle(np.exp(1j * (a.phase.astype(np.float64) - b.phase.astype(np.float64))))
+    assert np.sqrt(np.mean(dphi ** 2)) <= 2e-5
+
+
+def test_dense_gs_4096_properties(cuda):
+    """GS on a dense 4096^2 target: Parseval (ortho transform of a unit-norm near field), efficiency
+    non-decreasing over iterations (GS error-reduction property), phase range."""
+    from slmsuite_b200 import Hologram
+
+    rng = np.random.default_rng(3)
+    target = rng.random((4096, 4096), dtype=np.float32)
+    h = Hologram(target, phase=rng.uniform(-np.pi, np.pi, (4096, 4096)).astype(np.float32))
+    eff = []
+
+    def overlap(holo):
+        a = holo.amp_ff
+        eff.append(float(np.sum(a.astype(np.float64) * holo.target) ** 2 / np.sum(a.astype(np.float64) ** 2)))
+
+    h.optimize("GS", maxiter=1, verbose=False)
+    overlap(h)
+    for _ in range(4):
+        h.optimize("GS", maxiter=3, verbose=False)
+        overlap(h)
+    a = h.amp_ff.astype(np.float64)
+    assert abs(np.sum(a * a) - 1) < 1e-5
+    assert all(e1 >= e0 - 1e-6 for e0, e1 in zip(eff, eff[1:]))
+    assert eff[-1] > eff[0]
+    ph = h.phase
+    assert ph.min() >= -np.pi - 1e-6 and ph.max() <= np.pi + 1e-6
+
+
+def test_single_delta_gives_blaze_4096(cuda):
+    """reference tests/holography/test_algorithms.py:51-84 at 4096^2: one far-field pixel -> linear phase ramp."""
+    from slmsuite_b200 import Hologram
+
+    N = 4096
+    ky, kx = 1234, 3210
+    t = np.zeros((N, N), dtype=np.float32)
+    t[ky, kx] = 1
+    h = Hologram(t, phase=np.random.default_rng(4).uniform(-np.pi, np.pi, (N, N)).astype(np.float32))
+    h.optimize("WGS-Kim", maxiter=8, verbose=False, fix_phase_iteration=3)
+    y = np.arange(N, dtype=np.float64)[:, None] - N // 2
+    x = np.arange(N, dtype=np.float64)[None, :] - N // 2
+    blaze = 2 * np.pi * ((kx - N // 2) * x / N + (ky - N // 2) * y / N)
+    err = np.angle(np.exp(1j * (h.get_phase() - blaze)))
+    err = np.angle(np.exp(1j * (err - err.flat[0])))
+    assert np.allclose(err, 0, atol=1e-2)
+    a = h.amp_ff
+    assert a[ky, kx] > 0.999
+
+
+def test_fused_equals_stepped_2048(cuda):
+    from slmsuite_b200 import Hologram
+
+    shape, slm = (2048, 2048), (1080, 1920)
+    target = _spots(shape, 100, 5)
+    phase = np.random.default_rng(6).uniform(-np.pi, np.pi, slm).astype(np.float32)
+    a = Hologram(target, phase=phase, slm_shape=slm)
+    a.optimize("WGS-Leonardo", maxiter=10, verbose=False)
+    b = Hologram(target, phase=phase, slm_shape=slm)
+    b.optimize("WGS-Leonardo", maxiter=10, verbose=False, callback=lambda h: False)
+    assert rel_rmse(a.amp_ff, b.amp_ff) <= 1e-5
+    assert rel_rmse(a.weights, b.weights) <= 1e-5
+
+
+def test_spot_hologram_config3_runs_and_improves_uniformity(cuda):
+    """BASELINE configs[2]: 32x32 spot grid on 4096^2, WGS with per-spot feedback (shortened to 12 iterations)."""
+    from slmsuite_b200 import SpotHologram
+
+    h = SpotHologram.make_rectangular_array((4096, 4096), array_shape=(32, 32), array_pitch=(64, 64), basis="knm")
+    h.reset_phase(np.random.default_rng(7).uniform(-np.pi, np.pi, (4096, 4096)).astype(np.float32))
+    h.optimize("WGS-Leonardo", maxiter=12, verbose=False, feedback="computational_spot",
+               stat_groups=["computational_spot"])
+    st = h.stats["stats"]["computational_spot"]
+    assert st["uniformity"][-1] > st["uniformity"][1]
+    assert st["efficiency"][-1] > 0.5
+
+
+def test_batch_config4_slice(cuda):
+    """BASELINE configs[3] shape (2048^2 holograms, GS) with a batch of 4: equals four single holograms."""
+    from slmsuite_b200 import Hologram, HologramBatch
+
+    B, N = 4, 2048
+    T = np.stack([_spots((N, N), 100, 100 + b) for b in range(B)])
+    P = np.stack([np.random.default_rng(200 + b).uniform(-np.pi, np.pi, (N, N)).astype(np.float32) for b in range(B)])
+    hb = HologramBatch(T, phase=P)
+    hb.optimize("GS", maxiter=6, verbose=False)
+    ph = hb.phase
+    for b in (0, 3):
+        h = Hologram(T[b], phase=P[b])
+        h.optimize("GS", maxiter=6, verbose=False)
+        assert np.allclose(ph[b], h.phase, atol=1e-5)
+
+
+def test_8192_config5_shape_runs(cuda):
+    """BASELINE configs[4] shape: 8192^2 padded field, 10k random spots, WGS-Leonardo (3 iterations)."""
+    from slmsuite_b200 import SpotHologram
+
+    v = np.random.default_rng(5).uniform(64, 8192 - 64, (2, 10000))
+    h = SpotHologram((8192, 8192), v, basis="knm")
+    h.reset_phase(np.random.default_rng(8).uniform(-np.pi, np.pi, (8192, 8192)).astype(np.float32))
+    h.optimize("WGS-Leonardo", maxiter=3, verbose=False, feedback="computational_spot")
+    a = h.amp_ff.astype(np.float64)
+    assert abs(np.sum(a * a) - 1) < 1e-5
+    assert h.iter == 3

@@ -69,6 +69,8 @@ typedef struct {
     int mraf;               /* target has NaN noise region, _hologram.py:1495-1548 */
     int mraf_has_factor;    /* flags["mraf_factor"] is not None */
     float mraf_factor;
+    int feedback;           /* 0: pixel feedback ("computational"); 1: per-spot window feedback ("computational_spot") */
+    int spot_width;         /* spot_integration_width_knm, _spots.py:1292-1297 (feedback == 1) */
 } slmgs_params;
 
 SLMGS_API int slmgs_version(void);
@@ -105,8 +107,10 @@ SLMGS_API int slmgs_get_nearfield(slmgs_ctx*, float* nearfield_c64);      /* [B]
 /* optimize_gs with callback=None and no per-iteration statistics (:1465-1493):
  * n_iter iterations, then _populate_results (:934-949).  params[i] are the flags of iteration i
  * (the host runs the WGS-Kim state machine of :1556-1585, which only depends on the iteration
- * count in this mode).  Supports GS, WGS-Leonardo/Kim/Wu/tanh with pixel ("computational")
- * feedback and MRAF with GS; everything else goes through the stepped entry points. */
+ * count in this mode).  GS, WGS-Leonardo/Kim/Wu/tanh with pixel feedback and MRAF with GS run two kernels
+ * per iteration; weight updates with a global dependency inside the iteration (WGS-Nogrette's mean, per-spot
+ * window feedback, MRAF + WGS) run a forward column pass for |farfield| first, then the update kernels, then
+ * the fused kernels.  Callbacks and per-iteration statistics go through the stepped entry points. */
 SLMGS_API int slmgs_run(slmgs_ctx*, const slmgs_params* params, int n_iter, int populate);
 
 /* ---- stepped loop (callbacks, statistics, Nogrette, spot feedback, MRAF + WGS) ------------- */

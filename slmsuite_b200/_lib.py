@@ -40,6 +40,8 @@ class Params(C.Structure):
         ("mraf", C.c_int),
         ("mraf_has_factor", C.c_int),
         ("mraf_factor", C.c_float),
+        ("feedback", C.c_int),
+        ("spot_width", C.c_int),
     ]
 
 

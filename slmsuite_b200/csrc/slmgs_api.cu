@@ -648,6 +648,9 @@ static int check_params(slmgs_ctx* c, const slmgs_params* p) {
 // ------------------------------------------------------------------------------------------
 // fused loop
 // ------------------------------------------------------------------------------------------
+static int update_weights_pixel_impl(slmgs_ctx* c, const slmgs_params* p);
+static int update_weights_spot_impl(slmgs_ctx* c, const slmgs_params* p, int width);
+
 extern "C" int slmgs_run(slmgs_ctx* c, const slmgs_params* params, int n_iter, int populate) {
     CHECK_CTX(c);
     if (n_iter < 0) return fail(c, SLMGS_ERR_INVALID, "n_iter < 0");
@@ -655,34 +658,44 @@ extern "C" int slmgs_run(slmgs_ctx* c, const slmgs_params* params, int n_iter, i
     for (int i = 0; i < n_iter; ++i) {
         int e = check_params(c, params + i);
         if (e) return e;
-        if (params[i].update_weights) {
-            if (params[i].method == SLMGS_GS) return fail(c, SLMGS_ERR_INVALID, "GS has no weight update");
-            if (params[i].method == SLMGS_WGS_NOGRETTE)
-                return fail(c, SLMGS_ERR_INVALID, "WGS-Nogrette needs a global mean: use the stepped entry points");
-            if (params[i].mraf)
-                return fail(c, SLMGS_ERR_INVALID, "MRAF with a weight update needs normalised weights: use the stepped entry points");
-        }
+        if (params[i].update_weights && params[i].method == SLMGS_GS) return fail(c, SLMGS_ERR_INVALID, "GS has no weight update");
+        if (params[i].update_weights && params[i].feedback == 1 && c->n_spots < 1)
+            return fail(c, SLMGS_ERR_STATE, "spot feedback without slmgs_set_spots");
     }
     int e;
     if (n_iter > 0) {
         RowArgs ra = row_args(c);
         if ((e = run_row(c, ROW_FIRST, ra))) return e;
         for (int i = 0; i < n_iter; ++i) {
+            const slmgs_params* p = params + i;
             ColArgs ca = col_args(c);
-            apply_params(ca, params + i);
-            ca.wgs_update = params[i].update_weights;
+            apply_params(ca, p);
+            // a weight update is done inside the fused kernel when it has no global dependency within the
+            // iteration (the L2 renormalisation is deferred by one kernel, see DESIGN.md "Lazy normalisation")
+            const bool in_kernel = p->update_weights && p->feedback == 0 && !p->mraf &&
+                                   (p->method == SLMGS_WGS_LEONARDO || p->method == SLMGS_WGS_KIM ||
+                                    p->method == SLMGS_WGS_WU || p->method == SLMGS_WGS_TANH);
+            const bool need_amp = p->update_weights && !in_kernel;
+            const bool need_phase = ca.phase_mode == PHASE_COMPUTE_STORE;
+            if (need_amp || need_phase) {
+                // one forward column pass for |farfield| (global-dependency updates: Nogrette mean, per-spot
+                // windows, MRAF + WGS) and/or angle(farfield) (the WGS-Kim iteration that fixes the phase)
+                ColArgs fa = col_args(c);
+                fa.store_ampff = need_amp;
+                fa.store_phaseff = need_phase;
+                if ((e = run_col(c, COL_FWD, fa))) return e;
+                if (need_phase) ca.phase_mode = PHASE_STORED;
+            }
+            if (need_amp) {
+                if (p->feedback == 1) e = update_weights_spot_impl(c, p, p->spot_width);
+                else e = update_weights_pixel_impl(c, p);
+                if (e) return e;
+            }
+            ca.wgs_update = in_kernel ? 1 : 0;
             ca.w_in_slot = c->w_pending;
             if (ca.wgs_update) {
                 ca.w_out_slot = (c->w_pending == ACC_W0) ? ACC_W1 : ACC_W0;
                 if ((e = zero_slot(c, ca.w_out_slot))) return e;
-            }
-            if (ca.phase_mode == PHASE_COMPUTE_STORE) {
-                // the iteration that fixes the far-field phase (WGS-Kim): keep angle(farfield) with one extra
-                // forward column pass, then constrain against the stored phase
-                ColArgs fa = col_args(c);
-                fa.store_phaseff = 1;
-                if ((e = run_col(c, COL_FWD, fa))) return e;
-                ca.phase_mode = PHASE_STORED;
             }
             if ((e = run_col(c, COL_FUSED, ca))) return e;
             if (ca.wgs_update) c->w_pending = ca.w_out_slot;
@@ -747,12 +760,9 @@ extern "C" int slmgs_get_farfield(slmgs_ctx* c, float* out) {
     return SLMGS_OK;
 }
 
-extern "C" int slmgs_update_weights(slmgs_ctx* c, const slmgs_params* p) {
-    CHECK_CTX(c);
-    int e = check_params(c, p);
-    if (e) return e;
-    if (p->method == SLMGS_GS) return fail(c, SLMGS_ERR_INVALID, "Weighting is only for WGS.");
-    if (!c->ff_valid) return fail(c, SLMGS_ERR_STATE, "update_weights needs a preceding forward()");
+// pixel feedback on amp_ff (must hold |farfield| of the current iteration): _hologram.py:1822-1879
+static int update_weights_pixel_impl(slmgs_ctx* c, const slmgs_params* p) {
+    int e;
     if ((e = resolve_weights(c))) return e;
     const long long P = (long long)c->H * c->W;
     // ||feedback||, _hologram.py:1830-1831
@@ -774,6 +784,15 @@ extern "C" int slmgs_update_weights(slmgs_ctx* c, const slmgs_params* p) {
     ElemArgs s = elem_args(c, nullptr, c->weights, P);
     s.slot0 = ACC_W0;
     return launch_elem<EW_SCALE>(c, s, c->B);
+}
+
+extern "C" int slmgs_update_weights(slmgs_ctx* c, const slmgs_params* p) {
+    CHECK_CTX(c);
+    int e = check_params(c, p);
+    if (e) return e;
+    if (p->method == SLMGS_GS) return fail(c, SLMGS_ERR_INVALID, "Weighting is only for WGS.");
+    if (!c->ff_valid) return fail(c, SLMGS_ERR_STATE, "update_weights needs a preceding forward()");
+    return update_weights_pixel_impl(c, p);
 }
 
 extern "C" int slmgs_set_spots(slmgs_ctx* c, int n, const int* x, const int* y, const float* spot_amp) {
@@ -804,14 +823,10 @@ static SpotArgs spot_args(slmgs_ctx* c, int width) {
     return a;
 }
 
-extern "C" int slmgs_update_weights_spot(slmgs_ctx* c, const slmgs_params* p, int width) {
-    CHECK_CTX(c);
-    int e = check_params(c, p);
-    if (e) return e;
-    if (p->method == SLMGS_GS) return fail(c, SLMGS_ERR_INVALID, "Weighting is only for WGS.");
+static int update_weights_spot_impl(slmgs_ctx* c, const slmgs_params* p, int width) {
+    int e;
     if (c->n_spots < 1) return fail(c, SLMGS_ERR_STATE, "no spots set");
     if (width < 1) return fail(c, SLMGS_ERR_INVALID, "width < 1");
-    if (!c->ff_valid) return fail(c, SLMGS_ERR_STATE, "update_weights_spot needs a preceding forward()");
     if ((e = resolve_weights(c))) return e;
     SpotArgs a = spot_args(c, width);
     a.wgs.method = p->method; a.wgs.p = p->feedback_exponent; a.wgs.f = p->feedback_factor;
@@ -821,6 +836,15 @@ extern "C" int slmgs_update_weights_spot(slmgs_ctx* c, const slmgs_params* p, in
     if (e) return e;
     c->launches++;
     return rt_check(c, launch_kernel<SpotUpdateKernel>(1, c->B, 1024, (1024 + 8) * sizeof(double), c->stream, a), "spot update launch");
+}
+
+extern "C" int slmgs_update_weights_spot(slmgs_ctx* c, const slmgs_params* p, int width) {
+    CHECK_CTX(c);
+    int e = check_params(c, p);
+    if (e) return e;
+    if (p->method == SLMGS_GS) return fail(c, SLMGS_ERR_INVALID, "Weighting is only for WGS.");
+    if (!c->ff_valid) return fail(c, SLMGS_ERR_STATE, "update_weights_spot needs a preceding forward()");
+    return update_weights_spot_impl(c, p, width);
 }
 
 extern "C" int slmgs_constrain_inverse(slmgs_ctx* c, const slmgs_params* p) {

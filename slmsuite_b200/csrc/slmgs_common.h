@@ -49,9 +49,18 @@ SLMGS_DEVICE float2 ld_stream(const float2* p) {
     asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
     return v;
 }
+SLMGS_DEVICE void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #else
 inline float ld_stream(const float* p) { return *p; }
 inline float2 ld_stream(const float2* p) { return *p; }
+inline void prefetch_l2(const void*) {}
+#endif
+
+// log2 of a power of two
+#if defined(__CUDACC__) && !defined(SLMGS_EMULATE)
+SLMGS_DEVICE int ilog2(int x) { return __ffs(x) - 1; }
+#else
+inline int ilog2(int x) { return __builtin_ctz((unsigned)x); }
 #endif
 
 SLMGS_HD cf cmake(float re, float im) { return make_float2(re, im); }

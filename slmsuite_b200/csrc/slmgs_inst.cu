@@ -29,17 +29,24 @@ int SLMGS_CAT(launch_row_, SLMGS_N)(int mode, int gx, int gy, int nthreads, rt_s
     return -1;
 }
 
-template <int VAR> static int launch_col_fused(int gx, int gy, int nthreads, rt_stream s, const ColArgs& a) {
-    typedef ColKernel<SLMGS_N, COL_FUSED, VAR> K;
+// a block of MAXT threads has a compile-time tile width (CT); smaller blocks derive it from blockDim
+template <int MODE, int VAR> static int launch_col_ct(int gx, int gy, int nthreads, rt_stream s, const ColArgs& a) {
+    typedef Fft<SLMGS_N> F;
+    constexpr int MAXT = 16384 / F::E;
+    if (nthreads == MAXT) {
+        typedef ColKernel<SLMGS_N, MODE, VAR, MAXT / F::TPL> K;
+        return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
+    }
+    typedef ColKernel<SLMGS_N, MODE, VAR, 0> K;
     return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
+}
+template <int VAR> static int launch_col_fused(int gx, int gy, int nthreads, rt_stream s, const ColArgs& a) {
+    return launch_col_ct<COL_FUSED, VAR>(gx, gy, nthreads, s, a);
 }
 
 int SLMGS_CAT(launch_col_, SLMGS_N)(int mode, int var, int gx, int gy, int nthreads, rt_stream s, const ColArgs& a) {
     switch (mode) {
-        case COL_FWD: {
-            typedef ColKernel<SLMGS_N, COL_FWD> K;
-            return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
-        }
+        case COL_FWD: return launch_col_ct<COL_FWD, VAR_GENERAL>(gx, gy, nthreads, s, a);
         case COL_FUSED:
             switch (var) {
                 case VAR_GS: return launch_col_fused<VAR_GS>(gx, gy, nthreads, s, a);

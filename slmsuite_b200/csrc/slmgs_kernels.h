@@ -194,8 +194,8 @@ template <int N, int MODE> struct RowKernel {
     }
     // SLM column of rolled x index n, or -1 outside the SLM
     static SLMGS_DEVICE int slm_col(const Args& a, int n) {
-        const int sc = ((n + (a.W >> 1)) & (a.W - 1)) - a.i2;
-        return (sc >= 0 && sc < a.w) ? sc : -1;
+        const unsigned sc = (unsigned)(((n + (a.W >> 1)) & (a.W - 1)) - a.i2);
+        return sc < (unsigned)a.w ? (int)sc : -1;
     }
     static SLMGS_DEVICE float amp_at(const Args& a, const ThreadId& id, const Loc& L, int sc) {
         return a.amp ? __ldg(a.amp + (long long)id.by * a.amp_bs + (long long)L.sr * a.w + sc) : a.amp_scalar;
@@ -346,7 +346,9 @@ struct ColArgs {
     int store_ampff, store_phaseff, store_farfield;  // COL_FWD outputs
 };
 
-template <int N, int MODE, int VAR = 0> struct ColKernel {
+// CT: columns per tile known at compile time (block of MAXT threads), 0 = derived from blockDim at run time
+// (small problems).  With CT fixed, every shared-memory access is base register + immediate offset.
+template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
     typedef Fft<N> F;
     typedef ColArgs Args;
     static constexpr int E = F::E, NS = F::NS;
@@ -366,9 +368,9 @@ template <int N, int MODE, int VAR = 0> struct ColKernel {
     };
     static SLMGS_DEVICE Loc locate(const Args& a, cf* smem, const ThreadId& id) {
         Loc L;
-        L.C = id.nthreads / F::TPL;
-        L.col = id.tid % L.C;
-        L.lt = id.tid / L.C;
+        L.C = CT > 0 ? CT : id.nthreads / F::TPL;  // a power of two
+        L.col = id.tid & (L.C - 1);
+        L.lt = id.tid >> ilog2(L.C);
         L.gc = id.bx * L.C + L.col;
         L.s = smem + L.col;
         L.fbase = (long long)id.by * a.fld_bs + L.gc;
@@ -377,30 +379,39 @@ template <int N, int MODE, int VAR = 0> struct ColKernel {
         L.tbase = (long long)id.by * a.target_bs + (long long)id.bx * a.H * L.C + L.col;
         return L;
     }
-    static SLMGS_DEVICE bool slm_row(const Args& a, int n) {
-        const int sr = ((n + (a.H >> 1)) & (a.H - 1)) - a.i0;
-        return sr >= 0 && sr < a.h;
-    }
-
+    // Rows of `fld` that hold the SLM (rolled index n): ((n + H/2) mod H) - i0 in [0, h).  Row n of butterfly
+    // b is b + (N/R0) m, so the row pointer advances by a constant and the test is one unsigned compare.
     static SLMGS_DEVICE void load_rows(State& st, const Args& a, const Loc& L) {
         constexpr int R = F::R0;
+        const bool full = a.h == a.H;
+        const long long step = (long long)(N / R) * a.W;
         SLMGS_UNROLL
         for (int u = 0; u < E / R; ++u) {
+            const int b = L.lt + F::TPL * u;
+            const cf* p = a.fld + L.fbase + (long long)b * a.W;
+            const unsigned r0 = (unsigned)(b + (a.H >> 1) - a.i0);
             SLMGS_UNROLL
             for (int m = 0; m < R; ++m) {
-                const int n = F::first_index(L.lt + F::TPL * u, m);
-                st.v[u * R + m] = slm_row(a, n) ? ld_stream(a.fld + L.fbase + (long long)n * a.W) : cmake(0.f, 0.f);
+                const unsigned sr = ((r0 + (unsigned)((N / R) * m) + (unsigned)a.i0) & (unsigned)(a.H - 1)) - (unsigned)a.i0;
+                st.v[u * R + m] = (full || sr < (unsigned)a.h) ? ld_stream(p) : cmake(0.f, 0.f);
+                p += step;
             }
         }
     }
     static SLMGS_DEVICE void store_rows(State& st, const Args& a, const Loc& L) {
         constexpr int R = F::R0;
+        const bool full = a.h == a.H;
+        const long long step = (long long)(N / R) * a.W;
         SLMGS_UNROLL
         for (int u = 0; u < E / R; ++u) {
+            const int b = L.lt + F::TPL * u;
+            cf* p = a.fld + L.fbase + (long long)b * a.W;
+            const unsigned r0 = (unsigned)(b + (a.H >> 1) - a.i0);
             SLMGS_UNROLL
             for (int m = 0; m < R; ++m) {
-                const int n = F::first_index(L.lt + F::TPL * u, m);
-                if (slm_row(a, n)) a.fld[L.fbase + (long long)n * a.W] = st.v[u * R + m];
+                const unsigned sr = ((r0 + (unsigned)((N / R) * m) + (unsigned)a.i0) & (unsigned)(a.H - 1)) - (unsigned)a.i0;
+                if (full || sr < (unsigned)a.h) *p = st.v[u * R + m];
+                p += step;
             }
         }
     }

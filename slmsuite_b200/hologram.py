@@ -487,11 +487,9 @@ class Hologram:
 
     def _fusable(self, callback):
         """
-        The fused two-kernel iteration is legal when nothing on the host needs the far field between
-        the transforms (SURVEY.md 7 "callback contract") and the weight update has no global
-        dependency inside the iteration: no callback, no statistics, pixel feedback, not Nogrette
-        (global mean), not MRAF + WGS (needs normalised weights next to the noise region), and no
-        efficiency-triggered Kim fixing (needs statistics).
+        The fused launch sequence (``slmgs_run``) is legal when nothing on the host needs the far field
+        between the transforms (SURVEY.md 7 "callback contract"): no callback, no statistics, device-side
+        feedback, and no efficiency-triggered Kim fixing (needs statistics).
         """
         fl = self.flags
         if callback is not None or len(fl["stat_groups"]) > 0:
@@ -501,13 +499,18 @@ class Hologram:
         m = fl["method"]
         if m == "GS":
             return True
-        if fl["feedback"] != "computational":
-            return False
-        if m == "WGS-Nogrette" or self._mraf_enabled():
+        if fl["feedback"] not in self._device_feedbacks():
             return False
         if m == "WGS-Kim" and fl.get("fix_phase_efficiency", None) is not None:
             return False
         return True
+
+    def _device_feedbacks(self):
+        return ("computational",)
+
+    def _feedback_params(self):
+        """(slmgs_params.feedback, slmgs_params.spot_width) for the current flags."""
+        return 0, 0
 
     def _iteration_params(self, mraf, stepped):
         """
@@ -555,6 +558,8 @@ class Hologram:
             mraf=int(mraf),
             mraf_has_factor=int(mf is not None),
             mraf_factor=float(mf if mf is not None else 1.0),
+            feedback=self._feedback_params()[0],
+            spot_width=self._feedback_params()[1],
         )
 
     def optimize_gs(self, iterations, callback):

@@ -190,6 +190,14 @@ class SpotHologram(Hologram):
         self._set_target_spots(reset_weights=reset_weights)
 
     # ------------------------------------------------------------------ weights
+    def _device_feedbacks(self):
+        return ("computational", "computational_spot")
+
+    def _feedback_params(self):
+        if self.flags.get("feedback") == "computational_spot":
+            return 1, int(self.spot_integration_width_knm)
+        return 0, 0
+
     def _update_weights(self, params):
         """_spots.py:1573-1624."""
         feedback = self.flags["feedback"]

@@ -50,6 +50,7 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
 
 
 def test_params_struct_layout_matches_header():
-    # slmgs_params: 3 ints, 2 floats, 2 ints, 1 float -> 32 bytes, no padding
-    assert ctypes.sizeof(_lib.Params) == 32
+    # slmgs_params: 3 ints, 2 floats, 2 ints, 1 float, 2 ints -> 40 bytes, no padding
+    assert ctypes.sizeof(_lib.Params) == 40
     assert _lib.Params.mraf_factor.offset == 28
+    assert _lib.Params.spot_width.offset == 36

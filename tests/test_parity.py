@@ -58,7 +58,8 @@ def test_case_matches_reference_golden(name, backend):
 
 
 @pytest.mark.parametrize("name", ["spots20_64_nostats_WGS-Leonardo", "spots20_64_nostats_WGS-Kim", "gs_dense_64",
-                                  "padded_kim_128", "mraf_gs_64"])
+                                  "padded_kim_128", "mraf_gs_64", "mraf_factor_leonardo_64", "spot_null_mraf_64",
+                                  "spot_random_64_pixelfb"])
 def test_fused_and_stepped_paths_agree(name, backend):
     """The same case through the fused two-kernel loop and through the stepped entry points
     (forced by a no-op callback) must agree: both implement _hologram.py:1465-1490."""
@@ -73,6 +74,48 @@ def test_fused_and_stepped_paths_agree(name, backend):
     assert rel_rmse(stepped["amp_ff"], fused["amp_ff"]) <= 1e-5
     assert rel_rmse(stepped["weights"], fused["weights"]) <= 1e-5
     assert int(stepped["fixed_phase"]) == int(fused["fixed_phase"])
+
+
+@pytest.mark.parametrize("method", ["WGS-Nogrette", "WGS-Wu", "WGS-tanh"])
+def test_fused_sequence_other_weightings_vs_oracle(method, backend):
+    """No statistics, no callback: the fused launch sequence (Nogrette: forward pass + update kernels + fused
+    kernels; Wu / tanh: in-kernel update with fast math) against the oracle."""
+    from oracle import gs_oracle
+    from slmsuite_b200 import Hologram
+
+    rng = np.random.default_rng(31)
+    target = np.zeros((64, 128), dtype=np.float32)
+    target[rng.integers(0, 64, 15), rng.integers(0, 128, 15)] = rng.uniform(0.5, 1.0, 15)
+    phase = rng.uniform(-np.pi, np.pi, (48, 100)).astype(np.float32)
+    kw = dict(method=method, maxiter=12, verbose=False)
+    a = Hologram(target, phase=phase, slm_shape=(48, 100))
+    a.optimize(**kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        b = gs_oracle.OracleHologram(target, phase=phase, slm_shape=(48, 100))
+        b.optimize(**kw)
+    assert rel_rmse(a.amp_ff, b.amp_ff) <= 1e-5
+    assert rel_rmse(a.weights, b.weights) <= 1e-5
+
+
+def test_spot_feedback_fused_sequence_vs_oracle(backend):
+    """SpotHologram with computational_spot feedback and no statistics runs the fused launch sequence."""
+    from oracle import gs_oracle
+    from slmsuite_b200 import SpotHologram
+
+    phase = np.random.default_rng(41).uniform(-np.pi, np.pi, (128, 128)).astype(np.float32)
+    kw = dict(method="WGS-Kim", maxiter=14, verbose=False, feedback="computational_spot", fix_phase_iteration=6)
+    a = SpotHologram.make_rectangular_array((128, 128), array_shape=(5, 4), array_pitch=(10, 14), basis="knm")
+    a.reset_phase(phase)
+    a.optimize(**kw)
+    b = gs_oracle.OracleSpotHologram.make_rectangular_array((128, 128), array_shape=(5, 4), array_pitch=(10, 14), basis="knm")
+    b.reset_phase(phase)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        b.optimize(**kw)
+    assert rel_rmse(a.amp_ff, b.amp_ff) <= 1e-5
+    assert rel_rmse(a.weights, b.weights) <= 1e-5
+    assert a.flags["fixed_phase"] == b.flags["fixed_phase"] is True
 
 
 def test_oracle_side_by_side_seeded(backend):

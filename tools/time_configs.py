@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Device-time per iteration of the BASELINE configs through the public API (CUDA events on the library stream)."""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from slmsuite_b200 import Hologram, HologramBatch, SpotHologram, _lib  # noqa: E402
+
+lib = _lib.use_library(_lib.DEFAULT_LIBRARY)
+
+
+def timed(h, reps, **kw):
+    h.optimize(verbose=False, **kw)  # warm
+    ms = C.c_float()
+    lib.slmgs_sync(h._ctx)
+    lib.slmgs_timer_start(h._ctx)
+    for _ in range(reps):
+        h.optimize(verbose=False, **kw)
+    lib.slmgs_timer_stop(h._ctx, C.byref(ms))
+    return ms.value / reps
+
+
+def spots(shape, n, seed):
+    rng = np.random.default_rng(seed)
+    pts = rng.integers(0, shape[0], (2, n))
+    t = np.zeros(shape, dtype=np.float32)
+    t[pts[1], pts[0]] = 1
+    return t
+
+
+which = sys.argv[1:] or ["1", "2", "2d", "3", "4", "5"]
+rng = np.random.default_rng(0)
+if "1" in which:
+    h = Hologram(rng.random((512, 512), dtype=np.float32), phase=rng.uniform(-3, 3, (512, 512)).astype(np.float32))
+    ms = timed(h, 5, method="GS", maxiter=30)
+    print(f"config1 GS 512^2 30 it: {ms:.3f} ms/optimize -> {30/ms*1e3:.0f} it/s")
+if "2" in which:
+    h = Hologram(spots((4096, 4096), 64, 1), phase=rng.uniform(-3, 3, (1152, 1920)).astype(np.float32), slm_shape=(1152, 1920))
+    ms = timed(h, 3, method="WGS-Kim", maxiter=50)
+    print(f"config2 WGS-Kim 4096^2 (slm 1152x1920) 50 it: {ms:.3f} ms/optimize -> {50/ms*1e3:.0f} it/s")
+if "2d" in which:
+    h = Hologram(rng.random((4096, 4096), dtype=np.float32), phase=rng.uniform(-3, 3, (4096, 4096)).astype(np.float32))
+    ms = timed(h, 3, method="GS", maxiter=50)
+    print(f"dense GS 4096^2 (slm 4096^2) 50 it: {ms:.3f} ms/optimize -> {50/ms*1e3:.0f} it/s  model frac {68*4096*4096*50/ms*1e3/6.538e12:.3f}")
+    ms = timed(h, 3, method="WGS-Kim", maxiter=50)
+    print(f"dense WGS-Kim 4096^2 50 it: {ms:.3f} ms/optimize -> {50/ms*1e3:.0f} it/s")
+if "3" in which:
+    h = SpotHologram.make_rectangular_array((4096, 4096), array_shape=(32, 32), array_pitch=(64, 64), basis="knm")
+    h.reset_phase(rng.uniform(-3, 3, (4096, 4096)).astype(np.float32))
+    ms = timed(h, 2, method="WGS-Leonardo", maxiter=100, feedback="computational_spot")
+    print(f"config3 SpotHologram 32x32 on 4096^2 WGS-Leonardo spot feedback 100 it: {ms:.3f} ms/optimize -> {100/ms*1e3:.0f} it/s")
+if "4" in which:
+    B = 8
+    T = np.stack([spots((2048, 2048), 100, 100 + b) for b in range(B)])
+    P = rng.uniform(-3, 3, (B, 2048, 2048)).astype(np.float32)
+    h = HologramBatch(T, phase=P)
+    ms = timed(h, 3, method="GS", maxiter=50)
+    print(f"config4 shard: batch of {B} 2048^2 GS 50 it: {ms:.3f} ms/optimize -> {B*50/ms*1e3:.0f} hologram-it/s per GPU")
+if "5" in which:
+    v = np.random.default_rng(5).uniform(64, 8192 - 64, (2, 10000))
+    t0 = time.time()
+    h = SpotHologram((8192, 8192), v, basis="knm")
+    h.reset_phase(rng.uniform(-3, 3, (8192, 8192)).astype(np.float32))
+    print(f"config5 ctor {time.time()-t0:.1f} s")
+    ms = timed(h, 1, method="WGS-Leonardo", maxiter=20, feedback="computational_spot")
+    print(f"config5 SpotHologram 10k spots 8192^2 WGS-Leonardo spot feedback 20 it: {ms:.3f} ms/optimize -> {20/ms*1e3:.0f} it/s")

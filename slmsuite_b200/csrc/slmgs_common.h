@@ -64,8 +64,14 @@ inline int ilog2(int x) { return __builtin_ctz((unsigned)x); }
 #endif
 
 SLMGS_HD cf cmake(float re, float im) { return make_float2(re, im); }
+#if defined(__CUDA_ARCH__) && !defined(SLMGS_EMULATE) && defined(SLMGS_PACKED_F32X2)
+// Blackwell packed FP32x2 (FADD2 / FFMA2): one issue slot per complex add / subtract
+SLMGS_HD cf cadd(cf a, cf b) { return __fadd2_rn(a, b); }
+SLMGS_HD cf csub(cf a, cf b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
+#else
 SLMGS_HD cf cadd(cf a, cf b) { return make_float2(a.x + b.x, a.y + b.y); }
 SLMGS_HD cf csub(cf a, cf b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 SLMGS_HD cf cmul(cf a, cf b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 // a * conj(b)
 SLMGS_HD cf cmulc(cf a, cf b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }

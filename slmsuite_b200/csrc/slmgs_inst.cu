@@ -18,7 +18,11 @@ int SLMGS_CAT(launch_row_, SLMGS_N)(int mode, int gx, int gy, int nthreads, rt_s
             return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
         }
         case ROW_FUSED: {
-            typedef RowKernel<SLMGS_N, ROW_FUSED> K;
+            if (a.store_phase) {
+                typedef RowKernel<SLMGS_N, ROW_FUSED, true> K;
+                return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
+            }
+            typedef RowKernel<SLMGS_N, ROW_FUSED, false> K;
             return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
         }
         case ROW_LAST: {

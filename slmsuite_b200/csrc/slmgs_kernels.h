@@ -161,7 +161,8 @@ struct RowArgs {
     int store_phase;     // ROW_FUSED: also write the phase this iteration
 };
 
-template <int N, int MODE> struct RowKernel {
+// STORE (ROW_FUSED only): this launch also writes the phase (last iteration of a fused run)
+template <int N, int MODE, bool STORE = false> struct RowKernel {
     typedef Fft<N> F;
     typedef RowArgs Args;
     static constexpr int E = F::E, NS = F::NS;
@@ -246,34 +247,38 @@ template <int N, int MODE> struct RowKernel {
     }
     // phase-only projection: _hologram.py:1026-1036 followed by :1000-1011 of the next iteration.
     // amp * exp(i * arctan2(im, re)) == amp * z / |z|  (z == 0 -> phase 0 -> amp)
-    template <bool REBUILD> static SLMGS_DEVICE void project(State& st, const Args& a, const ThreadId& id, const Loc& L) {
+    // REBUILD: also build the next near field (ROW_FUSED); WRITE: store the phase (last iteration / ROW_LAST).
+    // The hot variant (REBUILD, !WRITE) is branch-free: select instead of branch, no arctan2 in the code.
+    template <bool REBUILD, bool WRITE>
+    static SLMGS_DEVICE void project(State& st, const Args& a, const ThreadId& id, const Loc& L) {
         constexpr int R = F::R0;
+        const bool full = a.w == a.W;
         SLMGS_UNROLL
         for (int u = 0; u < E / R; ++u) {
             SLMGS_UNROLL
             for (int m = 0; m < R; ++m) {
                 const int n = F::first_index(L.lt + F::TPL * u, m);
-                const int sc = slm_col(a, n);
+                const unsigned scu = (unsigned)(((n + (a.W >> 1)) & (a.W - 1)) - a.i2);
+                const bool inside = L.active && (full || scu < (unsigned)a.w);
+                const int sc = inside ? (int)scu : 0;
                 const cf z = st.v[u * R + m];
-                cf val = cmake(0.f, 0.f);
-                if (L.active && sc >= 0) {
-                    if (!REBUILD || a.store_phase) {
+                if (WRITE) {
+                    if (inside) {
                         float ph = atan2f(z.y, z.x);
                         if (a.prop) ph -= __ldg(a.prop + (long long)L.sr * a.w + sc);
                         a.phase[L.pbase + sc] = ph;
                         if (!REBUILD && a.nearfield)
                             a.nearfield[(long long)id.by * a.phase_bs + (long long)L.sr * a.w + sc] = cscale(z, a.scale);
                     }
-                    if (REBUILD) {
-                        const float m2 = z.x * z.x + z.y * z.y;
-                        const float am = amp_at(a, id, L, sc);
-                        if (m2 > 0.f) {
-                            const float r = rsqrtf(m2) * am;
-                            val = cmake(z.x * r, z.y * r);
-                        } else {
-                            val = cmake(am, 0.f);
-                        }
-                    }
+                }
+                cf val = cmake(0.f, 0.f);
+                if (REBUILD) {
+                    const float m2 = z.x * z.x + z.y * z.y;
+                    const float am = a.amp ? (L.active ? __ldg(a.amp + (long long)id.by * a.amp_bs + (long long)L.sr * a.w + sc) : 0.f)
+                                           : a.amp_scalar;
+                    const float r = m2 > 0.f ? rsqrtf(m2) * am : 0.f;
+                    val = m2 > 0.f ? cmake(z.x * r, z.y * r) : cmake(am, 0.f);
+                    if (!inside) val = cmake(0.f, 0.f);
                 }
                 st.v[u * R + m] = val;
             }
@@ -289,14 +294,14 @@ template <int N, int MODE> struct RowKernel {
         } else if constexpr (MODE == ROW_LAST) {
             if constexpr (P == 0) load_spectrum(st, a, L);
             F::template inv_stage<NS - 1 - P>(st.v, L.lt, a.twA, a.twB, L.s, 1);
-            if constexpr (P == NS - 1) project<false>(st, a, id, L);
+            if constexpr (P == NS - 1) project<false, true>(st, a, id, L);
         } else {
             if constexpr (P == 0) load_spectrum(st, a, L);
             if constexpr (P < NS - 1) {
                 F::template inv_stage<NS - 1 - P>(st.v, L.lt, a.twA, a.twB, L.s, 1);
             } else if constexpr (P == NS - 1) {
                 F::template inv_stage<0>(st.v, L.lt, a.twA, a.twB, L.s, 1);
-                project<true>(st, a, id, L);
+                project<true, STORE>(st, a, id, L);
                 F::template fwd_stage<0>(st.v, L.lt, a.twA, a.twB, L.s, 1);
             } else {
                 F::template fwd_stage<P - (NS - 1)>(st.v, L.lt, a.twA, a.twB, L.s, 1);

@@ -10,7 +10,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from slmsuite_b200 import Hologram, HologramBatch, SpotHologram, _lib  # noqa: E402
 
-lib = _lib.use_library(_lib.DEFAULT_LIBRARY)
+lib = _lib.use_library(os.environ.get("SLMGS_LIB") or _lib.DEFAULT_LIBRARY)
 
 
 def timed(h, reps, **kw):

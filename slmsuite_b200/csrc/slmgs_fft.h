@@ -94,17 +94,64 @@ template <int N> struct Fft {
     static SLMGS_HD int first_index(int b, int m) { return b + (N / R0) * m; }
     static SLMGS_HD int last_index(int b, int m) { return b + (N / last_radix()) * m; }
 
-    // ---- compile-time loops --------------------------------------------------------------
-    template <int S, int DIR, int U, int K>
-    static SLMGS_DEVICE void fwd_store(cf* v, int lt, const cf* twA, const cf* twB, cf* s, int si) {
-        constexpr int R = radix<S>();
-        if constexpr (K < R) {
-            const int b = lt + TPL * U;
-            cf val = v[U * R + RegFFT<R>::pos(K)];
-            if (K > 0) val = cmul(val, twiddle<S>(twA, twB, b, K));
-            s[(sbase<S>(b) + K * sstride<S>()) * si] = val;
-            fwd_store<S, DIR, U, K + 1>(v, lt, twA, twB, s, si);
+    // ---- twiddle generation ---------------------------------------------------------------
+    // The R-1 twiddles w^k of a butterfly (w = table entry of exponent 1) are visited as fn(IC<k>, w^k).
+    // SLMGS_TW_PRODUCTS: only the powers of two are loaded (w, w^2, w^4, w^8, ...), the others are products of
+    // at most three loaded values (<= 2.5 ulp): 4 instead of 15 table loads per radix-16 stage, which takes
+    // load off the L1 data pipe that the shared-memory exchange already keeps half busy.
+    template <int K> struct IC {
+        static constexpr int value = K;
+    };
+    static constexpr int high_pow2(int g) { return g >= 16 ? 16 : g >= 8 ? 8 : g >= 4 ? 4 : g >= 2 ? 2 : 1; }
+    template <int S, int G, int NG, class Fn>
+    static SLMGS_DEVICE void tw_groups(cf* W, cf w1, cf w2, cf w3, int b, const cf* twA, const cf* twB, Fn& fn) {
+        if constexpr (G < NG) {
+            constexpr int hp = high_pow2(G);
+            if constexpr (hp == G) W[G] = twiddle<S>(twA, twB, b, 4 * G);
+            else W[G] = cmul(W[hp], W[G - hp]);
+            fn(IC<4 * G>(), W[G]);
+            fn(IC<4 * G + 1>(), cmul(W[G], w1));
+            fn(IC<4 * G + 2>(), cmul(W[G], w2));
+            fn(IC<4 * G + 3>(), cmul(W[G], w3));
+            tw_groups<S, G + 1, NG>(W, w1, w2, w3, b, twA, twB, fn);
         }
+    }
+    template <int S, int K, class Fn> static SLMGS_DEVICE void tw_table(int b, const cf* twA, const cf* twB, Fn& fn) {
+        if constexpr (K < radix<S>()) {
+            fn(IC<K>(), twiddle<S>(twA, twB, b, K));
+            tw_table<S, K + 1>(b, twA, twB, fn);
+        }
+    }
+    template <int S, class Fn> static SLMGS_DEVICE void for_each_twiddle(int b, const cf* twA, const cf* twB, Fn fn) {
+        constexpr int R = radix<S>();
+#ifdef SLMGS_TW_PRODUCTS
+        if constexpr (R >= 8) {
+            const cf w1 = twiddle<S>(twA, twB, b, 1);
+            const cf w2 = twiddle<S>(twA, twB, b, 2);
+            const cf w3 = cmul(w1, w2);
+            fn(IC<1>(), w1);
+            fn(IC<2>(), w2);
+            fn(IC<3>(), w3);
+            cf W[R / 4];
+            tw_groups<S, 1, R / 4>(W, w1, w2, w3, b, twA, twB, fn);
+        } else {
+            tw_table<S, 1>(b, twA, twB, fn);
+        }
+#else
+        tw_table<S, 1>(b, twA, twB, fn);
+#endif
+    }
+
+    // ---- compile-time loops --------------------------------------------------------------
+    template <int S, int U> static SLMGS_DEVICE void fwd_store_all(cf* v, int lt, const cf* twA, const cf* twB, cf* s, int si) {
+        constexpr int R = radix<S>();
+        const int b = lt + TPL * U;
+        cf* sp = s + sbase<S>(b) * si;
+        sp[0] = v[U * R + RegFFT<R>::pos(0)];
+        for_each_twiddle<S>(b, twA, twB, [&](auto k, cf w) {
+            constexpr int K = decltype(k)::value;
+            sp[K * sstride<S>() * si] = cmul(v[U * R + RegFFT<R>::pos(K)], w);
+        });
     }
     template <int S, int U, int K> static SLMGS_DEVICE void load_elems(cf* v, int lt, const cf* s, int si) {
         constexpr int R = radix<S>();
@@ -114,14 +161,12 @@ template <int N> struct Fft {
             load_elems<S, U, K + 1>(v, lt, s, si);
         }
     }
-    template <int S, int U, int K>
-    static SLMGS_DEVICE void inv_twiddle(cf* v, int lt, const cf* twA, const cf* twB) {
+    template <int S, int U> static SLMGS_DEVICE void inv_twiddle_all(cf* v, int lt, const cf* twA, const cf* twB) {
         constexpr int R = radix<S>();
-        if constexpr (K < R) {
-            const int b = lt + TPL * U;
-            v[U * R + K] = cmulc(v[U * R + K], twiddle<S>(twA, twB, b, K));
-            inv_twiddle<S, U, K + 1>(v, lt, twA, twB);
-        }
+        for_each_twiddle<S>(lt + TPL * U, twA, twB, [&](auto k, cf w) {
+            constexpr int K = decltype(k)::value;
+            v[U * R + K] = cmulc(v[U * R + K], w);
+        });
     }
     template <int S, int U, int K> static SLMGS_DEVICE void inv_store(cf* v, int lt, cf* s, int si) {
         constexpr int R = radix<S>();
@@ -150,7 +195,7 @@ template <int N> struct Fft {
         if constexpr (U < Q) {
             if constexpr (S > 0) load_elems<S, U, 0>(v, lt, s, si);
             RegFFT<R>::template run<1, 1>(v + U * R);
-            if constexpr (S < NS - 1) fwd_store<S, 1, U, 0>(v, lt, twA, twB, s, si);
+            if constexpr (S < NS - 1) fwd_store_all<S, U>(v, lt, twA, twB, s, si);
             fwd_stage_u<S, U + 1>(v, lt, twA, twB, s, si);
         }
     }
@@ -182,7 +227,7 @@ template <int N> struct Fft {
         if constexpr (U < Q) {
             if constexpr (S < NS - 1) {
                 load_elems<S, U, 0>(v, lt, s, si);
-                inv_twiddle<S, U, 1>(v, lt, twA, twB);
+                inv_twiddle_all<S, U>(v, lt, twA, twB);
             }
             RegFFT<R>::template run<-1, 1>(v + U * R);
             if constexpr (S > 0) inv_store<S, U, 0>(v, lt, s, si);

@@ -54,49 +54,62 @@ def make_inputs(seed):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region: NVML polled every ~5 ms from a thread
+    (nvidia-smi -lms as a fallback)."""
 
     def __init__(self, device):
         self.device = device
-        self.rows = []
-        self.proc = None
+        self.samples = []  # (t, sm_mhz, reasons bitmask)
+        self.smax = None
+        self.stop_flag = False
+        self.thread = None
+        self.mode = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            # torchrun sets CUDA_VISIBLE_DEVICES per rank only if asked to; LOCAL_RANK indexes the visible list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = int(vis.split(",")[self.device]) if vis and vis.split(",")[self.device].isdigit() else self.device
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+            self.mode = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.mode = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((time.perf_counter(), mhz, reasons))
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.05] or [r for (_, r) in self.rows]
-        for r in rows:
-            p = [x.strip() for x in r.split(",")]
-            try:
-                sm.append(float(p[0]))
-                smax = float(p[1])
-            except Exception:
-                continue
-            for name, val in zip(names, p[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if self.mode != "nvml":
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        nv = self.nv
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        reasons = sorted(k for k, bit in names.items() if any(s[2] & bit for s in inside))
+        return {"sm_mhz": float(np.median([s[1] for s in inside])) if inside else None, "sm_max_mhz": self.smax,
+                "reasons": reasons, "samples": len(inside)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -268,8 +281,7 @@ def run_b200(args, rank, local_rank, world):
     # ---- timed region: K steps, device events on the launching stream ---------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.3)
-    chk(lib.slmgs_profile_enable(ctx, 1))
+    time.sleep(0.05)
     launches0 = lib.slmgs_launch_count(ctx)
     barrier()
     w0 = time.perf_counter()
@@ -285,14 +297,21 @@ def run_b200(args, rank, local_rank, world):
     barrier()
     w1 = time.perf_counter()
     launches = lib.slmgs_launch_count(ctx) - launches0
-    prof_ms = (C.c_float * 6)()
-    prof_n = (C.c_int * 6)()
-    chk(lib.slmgs_profile_read(ctx, prof_ms, prof_n))
-    chk(lib.slmgs_profile_enable(ctx, 0))
     clocks = sampler.stop(w0, w1)
     total_ms = max_over_ranks(float(ms.value) + ag_ms)
     wall_ms = max_over_ranks(1e3 * (w1 - w0))
     total_launches = int(sum_over_ranks(float(launches)))
+
+    # ---- per-kernel durations: the same K steps again with CUDA events around every launch ----------
+    # (event records between kernels switch off programmatic dependent launch, so they stay out of the timed
+    # region above; same process, same inputs, immediately afterwards)
+    chk(lib.slmgs_profile_enable(ctx, 1))
+    for _ in range(args.steps):
+        step_resident()
+    prof_ms = (C.c_float * 6)()
+    prof_n = (C.c_int * 6)()
+    chk(lib.slmgs_profile_read(ctx, prof_ms, prof_n))
+    chk(lib.slmgs_profile_enable(ctx, 0))
 
     # ---- end-to-end: same steps through host buffers ---------------------------------------------
     barrier()
@@ -353,6 +372,8 @@ def run_b200(args, rank, local_rank, world):
         "actual_bytes_per_launch": actual, "actual_gbs": actual / (dom_ms * 1e-3) / 1e9,
         "actual_frac": actual / (dom_ms * 1e-3) / 1e9 / peak,
         "kernel_share_of_step": {k: v / tot for k, v in share.items()},
+        "measured": "CUDA events around every launch of the same K steps, repeated right after the timed region "
+                    "(event records between kernels disable programmatic dependent launch)",
         "kernels": kern,
         "iteration_model_frac": (76.0 * 9 + 80.0 * 40 + 68.0) / 50.0 * P * (value / world) / 1e9 / peak,
     }
@@ -388,6 +409,8 @@ def run_b200(args, rank, local_rank, world):
 
 
 def main():
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

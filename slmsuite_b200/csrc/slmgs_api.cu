@@ -129,6 +129,7 @@ struct slmgs_ctx {
     float* phase_saved;
     // timing
     bool profiling;
+    bool use_pdl;
 #ifndef SLMGS_EMULATE
     cudaEvent_t t0, t1;
     std::vector<cudaEvent_t> ev_pool;   // pairs
@@ -281,6 +282,7 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
     c->stream = nullptr;
     c->phase_saved = nullptr;
     c->profiling = false;
+    c->use_pdl = env_int("SLMGS_PDL", 1) != 0;
 #ifndef SLMGS_EMULATE
     c->t0 = c->t1 = nullptr;
     c->ev_used = 0;
@@ -560,6 +562,9 @@ static RowArgs row_args(slmgs_ctx* c) {
     a.scale = (float)(1.0 / sqrt((double)c->H * (double)c->W));
     a.H = c->H; a.W = c->W; a.h = c->h; a.w = c->w; a.i0 = c->i0; a.i2 = c->i2;
     a.store_phase = 0;
+    a.zero_acc = nullptr;
+    a.zero_bs = ACC_N;
+    a.pdl = (c->use_pdl && !c->profiling) ? 1 : 0;
     return a;
 }
 static ColArgs col_args(slmgs_ctx* c) {
@@ -586,6 +591,7 @@ static ColArgs col_args(slmgs_ctx* c) {
     a.wgs.p = 0.f; a.wgs.f = 0.f;
     a.wgs.inv_fnorm = (float)(1.0 / c->fnorm);
     a.wgs.neg_inv_mean = -1.0f;
+    a.pdl = (c->use_pdl && !c->profiling) ? 1 : 0;
     return a;
 }
 // profiling: bracket a launch with events from a pool (class k: 0..2 row modes, 3..5 column modes)
@@ -664,17 +670,24 @@ extern "C" int slmgs_run(slmgs_ctx* c, const slmgs_params* params, int n_iter, i
     }
     int e;
     if (n_iter > 0) {
+        // a weight update is done inside the fused kernel when it has no global dependency within the
+        // iteration (the L2 renormalisation is deferred by one kernel, see DESIGN.md "Lazy normalisation")
+        auto in_kernel_update = [&](const slmgs_params* p) {
+            return p->update_weights && p->feedback == 0 && !p->mraf &&
+                   (p->method == SLMGS_WGS_LEONARDO || p->method == SLMGS_WGS_KIM || p->method == SLMGS_WGS_WU ||
+                    p->method == SLMGS_WGS_TANH);
+        };
+        // the accumulator slot that receives sum(w^2) alternates; the row kernel that precedes a column kernel
+        // clears that kernel's slot (no memset node between the kernels)
+        auto out_slot_after = [&](int pending) { return pending == ACC_W0 ? ACC_W1 : ACC_W0; };
         RowArgs ra = row_args(c);
+        if (in_kernel_update(params)) ra.zero_acc = c->acc + out_slot_after(c->w_pending);
         if ((e = run_row(c, ROW_FIRST, ra))) return e;
         for (int i = 0; i < n_iter; ++i) {
             const slmgs_params* p = params + i;
             ColArgs ca = col_args(c);
             apply_params(ca, p);
-            // a weight update is done inside the fused kernel when it has no global dependency within the
-            // iteration (the L2 renormalisation is deferred by one kernel, see DESIGN.md "Lazy normalisation")
-            const bool in_kernel = p->update_weights && p->feedback == 0 && !p->mraf &&
-                                   (p->method == SLMGS_WGS_LEONARDO || p->method == SLMGS_WGS_KIM ||
-                                    p->method == SLMGS_WGS_WU || p->method == SLMGS_WGS_TANH);
+            const bool in_kernel = in_kernel_update(p);
             const bool need_amp = p->update_weights && !in_kernel;
             const bool need_phase = ca.phase_mode == PHASE_COMPUTE_STORE;
             if (need_amp || need_phase) {
@@ -693,13 +706,12 @@ extern "C" int slmgs_run(slmgs_ctx* c, const slmgs_params* params, int n_iter, i
             }
             ca.wgs_update = in_kernel ? 1 : 0;
             ca.w_in_slot = c->w_pending;
-            if (ca.wgs_update) {
-                ca.w_out_slot = (c->w_pending == ACC_W0) ? ACC_W1 : ACC_W0;
-                if ((e = zero_slot(c, ca.w_out_slot))) return e;
-            }
+            if (ca.wgs_update) ca.w_out_slot = out_slot_after(c->w_pending);
             if ((e = run_col(c, COL_FUSED, ca))) return e;
             if (ca.wgs_update) c->w_pending = ca.w_out_slot;
             ra.store_phase = (i == n_iter - 1);
+            ra.zero_acc = nullptr;
+            if (i + 1 < n_iter && in_kernel_update(params + i + 1)) ra.zero_acc = c->acc + out_slot_after(c->w_pending);
             if ((e = run_row(c, ROW_FUSED, ra))) return e;
         }
     }

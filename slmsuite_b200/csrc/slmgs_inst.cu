@@ -15,19 +15,19 @@ int SLMGS_CAT(launch_row_, SLMGS_N)(int mode, int gx, int gy, int nthreads, rt_s
     switch (mode) {
         case ROW_FIRST: {
             typedef RowKernel<SLMGS_N, ROW_FIRST> K;
-            return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
+            return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
         }
         case ROW_FUSED: {
             if (a.store_phase) {
                 typedef RowKernel<SLMGS_N, ROW_FUSED, true> K;
-                return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
+                return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
             }
             typedef RowKernel<SLMGS_N, ROW_FUSED, false> K;
-            return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
+            return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
         }
         case ROW_LAST: {
             typedef RowKernel<SLMGS_N, ROW_LAST> K;
-            return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
+            return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
         }
     }
     return -1;
@@ -39,10 +39,10 @@ template <int MODE, int VAR> static int launch_col_ct(int gx, int gy, int nthrea
     constexpr int MAXT = 16384 / F::E;
     if (nthreads == MAXT) {
         typedef ColKernel<SLMGS_N, MODE, VAR, MAXT / F::TPL> K;
-        return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
+        return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
     }
     typedef ColKernel<SLMGS_N, MODE, VAR, 0> K;
-    return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
+    return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
 }
 template <int VAR> static int launch_col_fused(int gx, int gy, int nthreads, rt_stream s, const ColArgs& a) {
     return launch_col_ct<COL_FUSED, VAR>(gx, gy, nthreads, s, a);
@@ -60,7 +60,7 @@ int SLMGS_CAT(launch_col_, SLMGS_N)(int mode, int var, int gx, int gy, int nthre
             }
         case COL_INV: {
             typedef ColKernel<SLMGS_N, COL_INV> K;
-            return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a);
+            return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
         }
     }
     return -1;

@@ -159,6 +159,9 @@ struct RowArgs {
     float scale;         // ROW_LAST near-field scale 1/sqrt(H W)
     int H, W, h, w, i0, i2;
     int store_phase;     // ROW_FUSED: also write the phase this iteration
+    double* zero_acc;    // accumulator slot to clear for the next column kernel ([B] slots, stride zero_bs), or nullptr
+    int zero_bs;
+    int pdl;             // launch with programmatic dependent launch
 };
 
 // STORE (ROW_FUSED only): this launch also writes the phase (last iteration of a fused run)
@@ -287,6 +290,9 @@ template <int N, int MODE, bool STORE = false> struct RowKernel {
 
     template <int P> static SLMGS_DEVICE void phase(State& st, const Args& a, cf* smem, const ThreadId& id) {
         const Loc L = locate(a, smem, id);
+        if constexpr (P == 0) {
+            if (a.zero_acc && id.bx == 0 && id.tid == 0) a.zero_acc[(long long)id.by * a.zero_bs] = 0.0;
+        }
         if constexpr (MODE == ROW_FIRST) {
             if constexpr (P == 0) build_nearfield(st, a, id, L);
             F::template fwd_stage<P>(st.v, L.lt, a.twA, a.twB, L.s, 1);
@@ -349,6 +355,7 @@ struct ColArgs {
     int mraf_has_factor;
     float mraf_factor;
     int store_ampff, store_phaseff, store_farfield;  // COL_FWD outputs
+    int pdl;              // launch with programmatic dependent launch
 };
 
 // CT: columns per tile known at compile time (block of MAXT threads), 0 = derived from blockDim at run time

@@ -14,9 +14,9 @@
 
 #include "slmgs_common.h"
 
+#include <string.h>
 #ifdef SLMGS_EMULATE
 #include <vector>
-#include <string.h>
 #endif
 
 namespace slmgs {
@@ -70,12 +70,18 @@ template <class K> __global__ void __launch_bounds__(K::MAXT, 1) slmgs_kernel(co
     id.bx = blockIdx.x;
     id.by = blockIdx.y;
     id.gx = gridDim.x;
+    // Programmatic dependent launch: let the next kernel of the stream start filling SMs as this grid's last
+    // wave drains (launch_dependents), and do not touch memory before the previous grid has completed and
+    // flushed (wait).  Both are no-ops when the kernel is launched without the PDL attribute.
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     run_phases<K, 0>(st, a, smem, id);
 }
 
 // returns cudaError_t as int
 template <class K>
-int launch_kernel(int gx, int gy, int nthreads, size_t smem_bytes, cudaStream_t stream, const typename K::Args& a) {
+int launch_kernel(int gx, int gy, int nthreads, size_t smem_bytes, cudaStream_t stream, const typename K::Args& a,
+                  bool pdl = false) {
     static bool attr_set[64] = {false};  // per instantiation, per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -83,6 +89,20 @@ int launch_kernel(int gx, int gy, int nthreads, size_t smem_bytes, cudaStream_t 
         cudaError_t e = cudaFuncSetAttribute(slmgs_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
         attr_set[dev & 63] = true;
+    }
+    if (pdl) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(gx, gy, 1);
+        cfg.blockDim = dim3(nthreads, 1, 1);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return (int)cudaLaunchKernelEx(&cfg, slmgs_kernel<K>, a);
     }
     slmgs_kernel<K><<<dim3(gx, gy, 1), dim3(nthreads, 1, 1), smem_bytes, stream>>>(a);
     return (int)cudaGetLastError();
@@ -98,7 +118,8 @@ inline void emu_phases(std::vector<typename K::State>& st, const typename K::Arg
 }
 
 template <class K>
-int launch_kernel(int gx, int gy, int nthreads, size_t smem_bytes, void* /*stream*/, const typename K::Args& a) {
+int launch_kernel(int gx, int gy, int nthreads, size_t smem_bytes, void* /*stream*/, const typename K::Args& a,
+                  bool /*pdl*/ = false) {
     std::vector<typename K::State> st(nthreads);
     std::vector<cf> smem(smem_bytes / sizeof(cf) + 2);
     for (int by = 0; by < gy; ++by)

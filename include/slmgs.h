@@ -101,7 +101,6 @@ SLMGS_API int slmgs_set_phase_ff(slmgs_ctx*, const float* phase_ff);
 SLMGS_API int slmgs_get_phase_ff(slmgs_ctx*, float* phase_ff);
 SLMGS_API int slmgs_get_amp_ff(slmgs_ctx*, float* amp_ff);
 SLMGS_API int slmgs_get_farfield(slmgs_ctx*, float* farfield_c64);        /* interleaved re/im, ortho-scaled */
-SLMGS_API int slmgs_get_nearfield(slmgs_ctx*, float* nearfield_c64);      /* [B][h][w] crop of ifft2 result (ROW_LAST), interleaved */
 
 /* ---- fused loop -------------------------------------------------------------------------- */
 /* optimize_gs with callback=None and no per-iteration statistics (:1465-1493):

@@ -107,7 +107,6 @@ struct slmgs_ctx {
     // device state
     cf* fld;
     cf* farfield;     // lazily allocated
-    cf* nearfield;    // lazily allocated, [B][h][w]
     cf* stage_c;      // staging buffer for complex downloads (lazily allocated, B*H*W)
     float* stage_f;   // staging for rolled uploads/downloads (B*H*W floats)
     float *phase, *amp, *prop, *target, *weights, *phase_ff, *amp_ff;
@@ -268,7 +267,7 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
     c->sms = rt_sm_count();
     c->irow = size_info(W);
     c->icol = size_info(H);
-    c->fld = nullptr; c->farfield = nullptr; c->nearfield = nullptr; c->stage_c = nullptr; c->stage_f = nullptr;
+    c->fld = nullptr; c->farfield = nullptr; c->stage_c = nullptr; c->stage_f = nullptr;
     c->phase = c->amp = c->prop = c->target = c->weights = c->phase_ff = c->amp_ff = nullptr;
     c->twA_row = c->twB_row = c->twA_col = c->twB_col = nullptr;
     c->acc = nullptr; c->partial = nullptr;
@@ -338,7 +337,7 @@ extern "C" int slmgs_destroy(slmgs_ctx* c) {
     if (!c) return SLMGS_OK;
     rt_set_device(c->device);
     if (c->stream) rt_sync(c->stream);
-    void* ptrs[] = {c->fld, c->farfield, c->nearfield, c->stage_c, c->stage_f, c->phase, c->amp, c->prop, c->target,
+    void* ptrs[] = {c->fld, c->farfield, c->stage_c, c->stage_f, c->phase, c->amp, c->prop, c->target,
                     c->weights, c->phase_ff, c->amp_ff, c->twA_row, c->twB_row, c->twA_col, c->twB_col, c->acc,
                     c->partial, c->spot_x, c->spot_y, c->spot_amp, c->spot_pw, c->phase_saved};
     for (void* p : ptrs)
@@ -873,12 +872,6 @@ extern "C" int slmgs_constrain_inverse(slmgs_ctx* c, const slmgs_params* p) {
     if ((e = run_row(c, ROW_LAST, ra))) return e;
     c->ff_valid = false;
     return SLMGS_OK;
-}
-
-extern "C" int slmgs_get_nearfield(slmgs_ctx* c, float* out) {
-    CHECK_CTX(c);
-    if (!out) return fail(c, SLMGS_ERR_INVALID, "nearfield is NULL");
-    return fail(c, SLMGS_ERR_STATE, "nearfield download is not kept by the fused loop; rebuild it from get_phase() and amp");
 }
 
 // ------------------------------------------------------------------------------------------

@@ -41,6 +41,12 @@ template <int MODE, int VAR> static int launch_col_ct(int gx, int gy, int nthrea
         typedef ColKernel<SLMGS_N, MODE, VAR, MAXT / F::TPL> K;
         return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
     }
+    if constexpr (MAXT / F::TPL >= 2) {
+        if (nthreads == MAXT / 2) {  // half-size blocks (two per SM) for zero-padded problems
+            typedef ColKernel<SLMGS_N, MODE, VAR, MAXT / F::TPL / 2> K;
+            return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
+        }
+    }
     typedef ColKernel<SLMGS_N, MODE, VAR, 0> K;
     return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
 }

@@ -61,7 +61,12 @@ SLMGS_HD float wgs_ratio(float famp, float t, const WgsParams& q) {
 // point-wise code small enough for 64 registers / the instruction cache.  The stepped path uses the
 // accurate library functions.
 #if defined(__CUDACC__) && !defined(SLMGS_EMULATE)
-SLMGS_DEVICE float fast_pow(float x, float y) { return exp2f(y * __log2f(x)); }
+SLMGS_DEVICE float fast_pow(float x, float y) {
+    float l, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y * l));
+    return r;
+}
 SLMGS_DEVICE float fast_exp(float x) { return __expf(x); }
 SLMGS_DEVICE float fast_tanh(float x) {
     x = fminf(fmaxf(x, -15.0f), 15.0f);
@@ -176,6 +181,18 @@ template <int N, int MODE, bool STORE = false> struct RowKernel {
     };
 
     static size_t smem_bytes(int nthreads) { return NS > 1 ? (size_t)(nthreads / F::TPL) * F::PADN * sizeof(cf) : 0; }
+
+#ifndef SLMGS_EMULATE
+    // Lines are independent: only the TPL threads of one line exchange data, so they synchronise on their own
+    // named barrier (one per line) instead of the whole block when a line owns whole warps.
+    static SLMGS_DEVICE void barrier(const ThreadId& id) {
+        if constexpr (F::TPL >= 128) {
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + id.tid / F::TPL), "n"(F::TPL) : "memory");
+        } else {
+            __syncthreads();
+        }
+    }
+#endif
 
     struct Loc {
         int lt, sr, fr;  // thread-in-line, SLM row (may be >= h: idle), field row
@@ -371,6 +388,10 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
     };
 
     static size_t smem_bytes(int nthreads) { return NS > 1 ? (size_t)(nthreads / F::TPL) * F::PADN * sizeof(cf) : 0; }
+
+#ifndef SLMGS_EMULATE
+    static SLMGS_DEVICE void barrier(const ThreadId&) { __syncthreads(); }
+#endif
 
     struct Loc {
         int lt, col, C;  // thread-in-line, column inside the tile, columns per tile

@@ -55,7 +55,7 @@ template <class K, int P>
 SLMGS_DEVICE void run_phases(typename K::State& st, const typename K::Args& a, cf* smem, const ThreadId& id) {
     K::template phase<P>(st, a, smem, id);
     if constexpr (P + 1 < K::NPHASE) {
-        __syncthreads();
+        K::barrier(id);
         run_phases<K, P + 1>(st, a, smem, id);
     }
 }

@@ -41,6 +41,9 @@ template <int OP> struct ElemKernel {
     static constexpr int MAXT = 256;
     static constexpr int NPHASE = 1;
     struct State {};
+#ifndef SLMGS_EMULATE
+    static SLMGS_DEVICE void barrier(const ThreadId&) { __syncthreads(); }
+#endif
 
     template <int P> static SLMGS_DEVICE void phase(State&, const Args& a, cf*, const ThreadId& id) {
         double* acc = a.acc ? a.acc + (long long)id.by * a.acc_bs : nullptr;
@@ -120,6 +123,9 @@ struct Stats2Args {
 };
 
 struct Stats2Kernel {
+#ifndef SLMGS_EMULATE
+    static SLMGS_DEVICE void barrier(const ThreadId&) { __syncthreads(); }
+#endif
     typedef Stats2Args Args;
     static constexpr int MAXT = 256;
     static constexpr int NPHASE = 2;
@@ -189,6 +195,9 @@ struct SpotArgs {
 };
 
 struct SpotGatherKernel {
+#ifndef SLMGS_EMULATE
+    static SLMGS_DEVICE void barrier(const ThreadId&) { __syncthreads(); }
+#endif
     typedef SpotArgs Args;
     static constexpr int MAXT = 256;
     static constexpr int NPHASE = 1;
@@ -218,6 +227,9 @@ struct SpotGatherKernel {
 
 // single block per hologram
 struct SpotUpdateKernel {
+#ifndef SLMGS_EMULATE
+    static SLMGS_DEVICE void barrier(const ThreadId&) { __syncthreads(); }
+#endif
     typedef SpotArgs Args;
     static constexpr int MAXT = 1024;
     static constexpr int NPHASE = 7;

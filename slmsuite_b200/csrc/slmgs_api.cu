@@ -212,6 +212,7 @@ static void choose_geometry(slmgs_ctx* c) {
         // two resident blocks per SM (<= 512 threads, <= ~70 KB shared memory each) overlap one block's
         // global-memory phases with the other's butterflies: measured 108 vs 124 us at 4096^2 on B200
         int nt = li.maxt > 512 && li.tpl <= 512 ? 512 : li.maxt;
+        while (nt > lo && (size_t)(nt / li.tpl) * li.padn * sizeof(cf) > 113 * 1024) nt >>= 1;  // N = 8192: one line per block
         while (nt > lo) {
             const int lines = nt / li.tpl;
             const long long blocks = (long long)((c->h + lines - 1) / lines) * c->B;

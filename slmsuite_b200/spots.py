@@ -198,6 +198,23 @@ class SpotHologram(Hologram):
             return 1, int(self.spot_integration_width_knm)
         return 0, 0
 
+    def _check_windows(self):
+        """analysis.take(clip=False) semantics (analysis/__init__.py:133-183): negative window indices wrap,
+        indices past the end raise IndexError.  Checked on the host before the device gathers."""
+        w = int(self.spot_integration_width_knm)
+        hi = (-((w - 1) // 2) if w % 2 else -(w // 2)) + w - 1
+        x, y = self.spot_knm_rounded[0], self.spot_knm_rounded[1]
+        if np.any(x + hi >= self.shape[1]) or np.any(y + hi >= self.shape[0]):
+            bad = int(max(np.max(x + hi) - self.shape[1], np.max(y + hi) - self.shape[0])) + max(self.shape)
+            raise IndexError(f"index {bad} is out of bounds for the spot integration windows of width {w} "
+                             f"in a far field of shape {self.shape}")
+
+    def _iteration_params(self, mraf, stepped):
+        p = super()._iteration_params(mraf, stepped)
+        if p.update_weights and p.feedback == 1:
+            self._check_windows()
+        return p
+
     def _update_weights(self, params):
         """_spots.py:1573-1624."""
         feedback = self.flags["feedback"]

@@ -185,3 +185,78 @@ def test_spot_hologram_construction_and_errors(emu):
         SpotHologram((64, 64), np.array([[0.01], [0.01]]), basis="kxy")
     one = SpotHologram((64, 64), (20, 30), basis="knm")
     assert one.spot_integration_width_knm == 3 and one.spot_knm.shape == (2, 1)
+
+
+def test_state_roundtrips_and_repeated_optimize(emu):
+    from slmsuite_b200 import Hologram
+
+    rng = np.random.default_rng(9)
+    t = _spots((64, 128), 7, seed=2)
+    h = Hologram(t, phase=rng.uniform(-3, 3, (40, 100)).astype(np.float32), slm_shape=(40, 100))
+    w = rng.random((64, 128)).astype(np.float32)
+    h.set_weights(w)
+    assert np.array_equal(h.get_weights(), w)          # centred <-> rolled tile-major layout round trip
+    h.weights = w * 2
+    assert np.array_equal(h.weights, w * 2)
+    pf = rng.uniform(-3, 3, (64, 128)).astype(np.float32)
+    h.phase_ff = pf
+    assert np.array_equal(h.phase_ff, pf)
+    h.phase_ff = None
+    assert h.phase_ff is None
+    h.reset_weights()
+    assert np.array_equal(h.weights, np.nan_to_num(h.target, nan=0))
+    # maxiter=0 still populates the far field of the current phase (_hologram.py:1493)
+    h.optimize("GS", maxiter=0, verbose=False)
+    assert h.iter == 0 and h.amp_ff is not None and abs(float(np.sum(np.square(h.amp_ff))) - 1) < 1e-5
+    # two optimize calls of 5 iterations == one call of 10 (state lives on the device between calls)
+    a = Hologram(t, phase=np.zeros((40, 100), np.float32) + 0.3, slm_shape=(40, 100))
+    b = Hologram(t, phase=np.zeros((40, 100), np.float32) + 0.3, slm_shape=(40, 100))
+    a.optimize("WGS-Leonardo", maxiter=5, verbose=False)
+    a.optimize("WGS-Leonardo", maxiter=5, verbose=False)
+    b.optimize("WGS-Leonardo", maxiter=10, verbose=False)
+    assert a.iter == b.iter == 10
+    assert np.allclose(a.phase, b.phase, atol=3e-5) and np.allclose(a.weights, b.weights, rtol=1e-4, atol=1e-8)
+    # reset() restores weights / iteration count / statistics, keeps the flags
+    a.reset(reset_phase=False)
+    assert a.iter == 0 and a.stats == {"method": [], "flags": {}, "stats": {}} and a.amp_ff is None
+    assert a.flags["method"] == "WGS-Leonardo"
+    assert np.array_equal(a.weights, np.nan_to_num(a.target, nan=0))
+
+
+def test_set_target_renormalises_and_farfield_accessor(emu):
+    from slmsuite_b200 import Hologram
+
+    h = Hologram(_spots((64, 64), 4), phase=np.zeros((64, 64), np.float32))
+    t2 = -3.0 * _spots((64, 64), 9, seed=5)                       # abs + L2 normalisation, _hologram.py:760-766
+    h.set_target(t2, reset_weights=True)
+    assert np.all(h.target >= 0) and np.isclose(np.sqrt(np.sum(np.square(h.target))), 1, rtol=1e-6)
+    assert np.array_equal(h.weights, h.target)
+    ff = h.get_farfield()
+    assert ff.dtype == np.complex64 and ff.shape == (64, 64)
+    # uniform amplitude, zero phase -> all the power in the centre pixel of the centred far field
+    assert np.isclose(abs(ff[32, 32]), 1, rtol=1e-5) and np.isclose(np.sum(np.abs(ff) ** 2), 1, rtol=1e-5)
+    assert np.allclose(h.amp_ff, np.abs(ff), atol=1e-7)
+    with pytest.raises(NotImplementedError):
+        h.get_farfield(shape=(128, 128))
+    with pytest.raises(ValueError, match="does not match hologram shape"):
+        h.set_target(np.zeros((32, 32), np.float32))
+
+
+def test_spot_window_edges_and_feedback_names(emu):
+    from slmsuite_b200 import SpotHologram
+
+    # a spot on the border: the 3x3 integration window wraps like NumPy negative indices (analysis.take, clip=False)
+    h = SpotHologram((64, 64), np.array([[0.0, 30.0, 40.0], [0.0, 20.0, 50.0]]), basis="knm")
+    h.reset_phase(np.random.default_rng(3).uniform(-3, 3, (64, 64)).astype(np.float32))
+    h.optimize("WGS-Leonardo", maxiter=5, verbose=False, feedback="computational_spot")
+    assert h.iter == 5 and np.isfinite(h.weights).all()
+    # a window that would run past the end of the array is an index error in the reference; here ValueError
+    h2 = SpotHologram((64, 64), np.array([[63.0, 30.0], [63.0, 20.0]]), basis="knm")
+    h2.reset_phase(np.zeros((64, 64), np.float32))
+    h2.optimize("GS", maxiter=1, verbose=False)
+    with pytest.raises(ValueError, match="out of bounds"):
+        h2._window_power(h2.spot_knm, 3)
+    with pytest.raises(IndexError, match="out of bounds"):   # the reference's analysis.take raises IndexError too
+        h2.optimize("WGS-Leonardo", maxiter=3, verbose=False, feedback="computational_spot")
+    with pytest.raises(NotImplementedError, match="camera"):
+        h.optimize("WGS-Leonardo", maxiter=2, verbose=False, feedback="experimental_spot")

@@ -102,6 +102,11 @@ SLMGS_API int slmgs_get_phase_ff(slmgs_ctx*, float* phase_ff);
 SLMGS_API int slmgs_get_amp_ff(slmgs_ctx*, float* amp_ff);
 SLMGS_API int slmgs_get_farfield(slmgs_ctx*, float* farfield_c64);        /* interleaved re/im, ortho-scaled */
 
+/* "next" row of the path: the gray levels SLM.set_phase() would display for get_phase(),
+ * hardware/slms/slm.py:636-690 + _phase2gray :695-743 (phase_scaling == 1): out[b][h][w] uint8 (bitdepth <= 8) or
+ * uint16; correction = optional float64 [h][w] wavefront correction (source["phase"]) or NULL. */
+SLMGS_API int slmgs_get_phase_gray(slmgs_ctx*, int bitdepth, const double* correction, void* out);
+
 /* ---- fused loop -------------------------------------------------------------------------- */
 /* optimize_gs with callback=None and no per-iteration statistics (:1465-1493):
  * n_iter iterations, then _populate_results (:934-949).  params[i] are the flags of iteration i

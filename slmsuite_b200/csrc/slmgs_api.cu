@@ -546,6 +546,36 @@ extern "C" int slmgs_get_amp_ff(slmgs_ctx* c, float* p) {
     return download_rolled(c, c->amp_ff, p, c->B);
 }
 
+extern "C" int slmgs_get_phase_gray(slmgs_ctx* c, int bitdepth, const double* correction, void* out) {
+    CHECK_CTX(c);
+    if (!out) return fail(c, SLMGS_ERR_INVALID, "out is NULL");
+    if (bitdepth < 1 || bitdepth > 16) return fail(c, SLMGS_ERR_INVALID, "bitdepth must be in [1, 16]");
+    const long long S = (long long)c->h * c->w;
+    const int out16 = bitdepth > 8;
+    const size_t out_bytes = (size_t)c->B * S * (out16 ? 2 : 1);
+    int e;
+    double* dcorr = nullptr;
+    void* dout = nullptr;
+    e = rt_check(c, rt_malloc(&dout, out_bytes), "device allocation");
+    if (!e && correction) {
+        e = dev_alloc(c, &dcorr, (size_t)S);
+        if (!e) e = rt_check(c, rt_h2d(dcorr, correction, (size_t)S * sizeof(double), c->stream), "h2d");
+    }
+    if (!e) {
+        ElemArgs a = elem_args(c, c->phase, dout, S);
+        a.corr = dcorr;
+        a.bitres = 1 << bitdepth;
+        a.factor = -((double)a.bitres / 2.0 / 3.14159265358979323846);
+        a.out16 = out16;
+        e = launch_elem<EW_PHASE2GRAY>(c, a, c->B);
+    }
+    if (!e) e = rt_check(c, rt_d2h(out, dout, out_bytes, c->stream), "d2h");
+    rt_sync(c->stream);
+    if (dout) rt_free(dout);
+    if (dcorr) rt_free(dcorr);
+    return e;
+}
+
 // ------------------------------------------------------------------------------------------
 // kernel argument builders
 // ------------------------------------------------------------------------------------------

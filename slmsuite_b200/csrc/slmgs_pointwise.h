@@ -17,6 +17,7 @@ enum {
     EW_STATS1 = 6,      // acc[slot0..2] += sum f^2, nansum t^2, nansum t f           (_stats.py:51-76)
     EW_FILL_NAN0 = 7,   // dst = nan_to_num(src, nan=0)                                (reset_weights, :608-614)
     EW_ABS_C64 = 8,     // dst(f32) = |src(c64)|
+    EW_PHASE2GRAY = 9,  // dst(u8/u16) = SLM gray level of get_phase() = src + pi (hardware/slms/slm.py:695-743)
 };
 
 struct ElemArgs {
@@ -34,6 +35,11 @@ struct ElemArgs {
     WgsParams wgs;
     int fnorm_slot;  // EW_WGS_UPDATE / EW_RATIO_SUM: inv_fnorm = 1/sqrt(acc[fnorm_slot]) if >= 0
     int mean_slot;   // EW_WGS_UPDATE: Nogrette mean = acc[mean_slot] / n
+    // EW_PHASE2GRAY
+    const double* corr;  // optional wavefront correction [n] (source["phase"], float64), shared by the batch
+    double factor;       // -(bitresolution / 2 pi)
+    int bitres;          // 2^bitdepth
+    int out16;           // output uint16 (bitdepth > 8) or uint8
 };
 
 template <int OP> struct ElemKernel {
@@ -96,6 +102,19 @@ template <int OP> struct ElemKernel {
             } else if (OP == EW_ABS_C64) {
                 const cf z = srcc[i];
                 dstf[i] = sqrtf(z.x * z.x + z.y * z.y);
+            } else if (OP == EW_PHASE2GRAY) {
+                // get_phase() is float32 (phase + pi, _hologram.py:807-811); SLM.set_phase copies it into a float64
+                // cache, adds the float64 correction, scales, rounds half-to-even, casts, subtracts one and masks.
+                // The reference's shift by a multiple of 2*bitresolution (slm.py:729-733) is a no-op modulo
+                // bitresolution and commutes with rint, so it is not reproduced.
+                const float g = srcf[i] + 3.14159274101257324f;
+                double p = (double)g;
+                if (a.corr) p += a.corr[i];
+                p = rint(p * a.factor);
+                const long long v = (long long)p - 1;
+                const unsigned u = (unsigned)(v & (long long)(a.bitres - 1));
+                if (a.out16) reinterpret_cast<unsigned short*>(a.dst)[(long long)id.by * a.dst_bs + i] = (unsigned short)u;
+                else reinterpret_cast<unsigned char*>(a.dst)[(long long)id.by * a.dst_bs + i] = (unsigned char)u;
             }
         }
         if (OP == EW_SUMSQ || OP == EW_RATIO_SUM) accum_add(acc + a.slot0, s0);

@@ -394,6 +394,27 @@ class Hologram:
     # north_star names the accessor extract_phase(); the reference's is get_phase() (SURVEY.md note)
     extract_phase = get_phase
 
+    def get_phase_gray(self, bitdepth=8, phase_correction=None):
+        """
+        The integer image ``SLM.set_phase(self.get_phase())`` would display on an SLM of ``bitdepth`` bits
+        (hardware/slms/slm.py:636-690 and ``_phase2gray`` :695-743, ``phase_scaling == 1``), computed on the
+        device and downloaded as uint8 (``bitdepth <= 8``) or uint16 -- a quarter / half of the bytes of
+        ``get_phase()``.  ``phase_correction`` is the SLM's ``source["phase"]`` (added when ``phase_correct``).
+        The result can be passed to the reference's ``SLM.set_phase``, which accepts integer data as is.
+        """
+        bitdepth = int(bitdepth)
+        if bitdepth < 1 or bitdepth > 16:
+            raise ValueError(f"bitdepth {bitdepth} not supported (1..16)")
+        corr = None
+        if phase_correction is not None:
+            corr = np.ascontiguousarray(phase_correction, dtype=np.float64)
+            if corr.shape != tuple(self.slm_shape):
+                raise ValueError(f"phase_correction of shape {corr.shape} is not of slm_shape {self.slm_shape}")
+        out = np.empty(self._bshape(self.slm_shape), dtype=np.uint8 if bitdepth <= 8 else np.uint16)
+        self._check(self._lib.slmgs_get_phase_gray(
+            self._ctx, bitdepth, None if corr is None else _lib.dptr(corr), out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def get_amp(self):
         """_hologram.py:813-826."""
         return self._amp

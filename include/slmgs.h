@@ -125,6 +125,17 @@ SLMGS_API int slmgs_update_weights_spot(slmgs_ctx*, const slmgs_params*, int wid
 SLMGS_API int slmgs_constrain_inverse(slmgs_ctx*, const slmgs_params*);    /* _gs_farfield_routines (constraint part) + _farfield2nearfield, :1587-1653, :1058-1073 */
 SLMGS_API int slmgs_populate(slmgs_ctx*);                                  /* _populate_results, :934-949 */
 
+/* ---- MultiplaneHologram ("next" row; _multiplane.py:255-286) ---------------------
+ * N child contexts (same slm_shape, same device, any padded shape) share one near-field phase.  Per iteration each
+ * child runs slmgs_forward, its own weight update, then slmgs_constrain_accumulate, which applies the far-field
+ * constraint, transforms back and ADDS weight * nearfield[crop] * exp(-i kernel) into `sum` ([batch][h][w] complex64
+ * on the device, obtained from slmgs_nearfield_sum_ptr of any child); slmgs_extract_phase_from_sum then sets
+ * phase = arctan2(sum) in every child.  Children must share a stream (slmgs_share_stream). */
+SLMGS_API int slmgs_share_stream(slmgs_ctx* ctx, slmgs_ctx* leader);
+SLMGS_API void* slmgs_nearfield_sum_ptr(slmgs_ctx* ctx);
+SLMGS_API int slmgs_constrain_accumulate(slmgs_ctx*, const slmgs_params*, float weight, void* sum, int first);
+SLMGS_API int slmgs_extract_phase_from_sum(slmgs_ctx*, const void* sum);
+
 /* ---- statistics ---------------------------------------------------------------------------- */
 /* _calculate_stats(amp_ff, target) pieces, _stats.py:7-116.  out[b][8] =
  * {sum f^2, nansum t^2, nansum t f, ratio min, ratio max, err min, err max, err sum} and

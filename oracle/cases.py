@@ -177,6 +177,72 @@ def _c(H, S):
     return h, dict(method="WGS-Leonardo", maxiter=10, feedback="computational_spot")
 
 
+# ---- MultiplaneHologram ---------------------------------------------------
+# builders: (Hologram, SpotHologram, MultiplaneHologram) -> (parent, optimize kwargs)
+MULTI_CASES = {}
+
+
+def _multi(name):
+    def deco(fn):
+        MULTI_CASES[name] = fn
+        return fn
+    return deco
+
+
+def _defocus(slm, strength):
+    y, x = np.mgrid[-1:1:slm[0] * 1j, -1:1:slm[1] * 1j]
+    return (strength * (x * x + y * y)).astype(np.float32)
+
+
+@_multi("multi_two_planes_gs")
+def _m(H, S, M):  # two depths of focus, same padded shape, array amplitude (the reference needs one)
+    slm = (32, 48)
+    ph = _phase(31, slm)
+    a = H(_spots_target(32, (64, 64), 5), amp=_gauss(slm), phase=ph, slm_shape=slm)
+    b = H(_spots_target(33, (64, 64), 7), amp=_gauss(slm), phase=ph, slm_shape=slm, propagation_kernel=_defocus(slm, 4.0))
+    return M([a, b]), dict(method="GS", maxiter=12)
+
+
+@_multi("multi_mixed_shapes_kim")
+def _m(H, S, M):  # different padded shapes (different ortho scales), weights, WGS-Kim past the fixing iteration
+    slm = (36, 60)
+    ph = _phase(34, slm)
+    amp = np.ones(slm, dtype=np.float32)
+    a = H(_spots_target(35, (64, 64), 6), amp=amp, phase=ph, slm_shape=slm)
+    b = H(_spots_target(36, (128, 128), 9), amp=amp, phase=ph, slm_shape=slm, propagation_kernel=_defocus(slm, -3.0))
+    c = S.make_rectangular_array((64, 128), array_shape=(3, 2), array_pitch=(12, 10), basis="knm", amp=amp, slm_shape=slm)
+    c.reset_phase(ph)
+    return M([a, b, c], weights=[1, 2, 1.5]), dict(method="WGS-Kim", maxiter=16, fix_phase_iteration=6)
+
+
+@_multi("multi_leonardo_stats")
+def _m(H, S, M):
+    slm = (64, 64)
+    ph = _phase(37, slm)
+    amp = _gauss(slm)
+    a = H(_spots_target(38, (64, 64), 8), amp=amp, phase=ph)
+    b = H(_spots_target(39, (64, 64), 8), amp=amp, phase=ph, propagation_kernel=_defocus(slm, 6.0))
+    return M([a, b], weights=[3, 1]), dict(method="WGS-Leonardo", maxiter=10, stat_groups=["computational"])
+
+
+def run_multi_case(name, Hologram, SpotHologram, MultiplaneHologram):
+    parent, kw = MULTI_CASES[name](Hologram, SpotHologram, MultiplaneHologram)
+    parent.optimize(verbose=False, **kw)
+    return parent
+
+
+def summarize_multi(parent):
+    out = {"phase": np.asarray(parent.phase, dtype=np.float32), "iter": np.int64(parent.iter)}
+    for i, h in enumerate(parent.holograms):
+        out[f"child{i}/amp_ff"] = np.asarray(h.amp_ff, dtype=np.float32)
+        out[f"child{i}/weights"] = np.asarray(h.weights, dtype=np.float32)
+        out[f"child{i}/fixed_phase"] = np.int64(bool(h.flags.get("fixed_phase", False)))
+        for group, d in h.stats["stats"].items():
+            if "efficiency" in d:
+                out[f"child{i}/stats/{group}/efficiency"] = np.asarray(d["efficiency"], dtype=np.float64)
+    return out
+
+
 def run_case(name, Hologram, SpotHologram):
     """Build, optimise (verbose off) and return the hologram."""
     holo, kw = CASES[name](Hologram, SpotHologram)

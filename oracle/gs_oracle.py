@@ -246,7 +246,9 @@ class OracleHologram:
         if amp is None:
             self.amp = 1 / np.sqrt(np.prod(self.slm_shape))
         else:
-            self.amp = np.array(amp, dtype=self.dtype)
+            # copy=None: no copy when the caller's array is already of this dtype, so the normalisation below
+            # happens IN the caller's array (reference quirk, visible when children share one amp array)
+            self.amp = np.array(amp, dtype=self.dtype, copy=None)
             self.amp *= 1 / l2norm(self.amp)
 
         # propagation kernel, _hologram.py:408-415
@@ -322,10 +324,12 @@ class OracleHologram:
         self.farfield = np.fft.fftshift(np.fft.fft2(np.fft.fftshift(self.nearfield), norm="ortho"))
         self.amp_ff = np.abs(self.farfield, out=self.amp_ff)
 
-    def _inverse(self):
+    def _inverse(self, extract=True):
         """_hologram.py:1058-1073 + 1026-1036."""
         i0, i1, i2, i3 = crop_bounds(self.shape, self.slm_shape)
         self.nearfield = np.fft.ifftshift(np.fft.ifft2(np.fft.ifftshift(self.farfield), norm="ortho"))
+        if not extract:
+            return
         self.phase = np.arctan2(self.nearfield.imag[i0:i1, i2:i3], self.nearfield.real[i0:i1, i2:i3],
                                 out=self.phase)
         if self.propagation_kernel is not None:
@@ -595,3 +599,90 @@ class OracleSpotHologram(OracleHologram):
                     np.sqrt(take_sum(pw, self.spot_knm, self.spot_integration_width_knm)),
                     self.spot_amp, total=np.sum(pw))
         return out
+
+
+# --------------------------------------------------------------------------- MultiplaneHologram
+class OracleMultiplaneHologram:
+    """
+    Reference ``MultiplaneHologram`` (_multiplane.py:29-75, :174-180, :214-286): N child holograms that share one
+    near-field phase; the parent sums the weighted complex child near fields and extracts one phase.
+    """
+
+    def __init__(self, holograms, weights=None):
+        self.holograms = holograms
+        first = holograms[0]
+        self.slm_shape = tuple(first.slm_shape)
+        self.shape = self.slm_shape
+        self.dtype, self.dtype_complex = first.dtype, first.dtype_complex
+        # parent state, _multiplane.py:62-75: amp and phase of the first child, shared by every child.  The parent
+        # constructor normalises the first child's amplitude array AGAIN, in place (_hologram.py:404-405 with
+        # copy=None), which can move its last bits; a scalar amp makes the reference constructor fail.
+        self.amp = first.amp
+        if not np.isscalar(self.amp):
+            self.amp *= 1 / l2norm(self.amp)
+        self.phase = np.array(first.phase, dtype=self.dtype)
+        self.propagation_kernel = None
+        self.target = None
+        for h in holograms:
+            h.amp = self.amp
+            h.phase = self.phase
+        if weights is None:
+            weights = np.ones(len(holograms), dtype=self.dtype)
+        self.weights = np.array(weights, dtype=self.dtype)
+        self.weights /= l2norm(self.weights)
+        self.flags = {}
+        self.iter = 0
+        self.stats = {"method": [], "flags": {}, "stats": {}}
+        self.nearfield = np.zeros(self.slm_shape, dtype=self.dtype_complex)
+
+    def __len__(self):
+        return len(self.holograms)
+
+    def get_phase(self):
+        return self.phase + np.pi
+
+    def _merge_flags(self, method, feedback, stat_groups, kw):
+        """_multiplane.py:174-180: parent flags first, then pushed into every child."""
+        OracleHologram._merge_flags(self, method, feedback, stat_groups, kw)
+        for h in self.holograms:
+            h.flags.update(self.flags)
+
+    def _forward(self):
+        """_multiplane.py:255-259."""
+        for h in self.holograms:
+            h.phase = self.phase
+            h._forward()
+            h.iter = self.iter
+
+    def _inverse(self):
+        """_multiplane.py:261-281."""
+        self.nearfield.fill(0)
+        for h, w in zip(self.holograms, self.weights):
+            h._inverse(extract=False)
+            i0, i1, i2, i3 = crop_bounds(h.shape, h.slm_shape)
+            if h.propagation_kernel is None:
+                self.nearfield += w * h.nearfield[i0:i1, i2:i3]
+            else:
+                self.nearfield += w * h.nearfield[i0:i1, i2:i3] * np.exp(-1j * h.propagation_kernel)
+            h.iter = self.iter
+        self.phase = np.arctan2(self.nearfield.imag, self.nearfield.real, out=self.phase)
+
+    def optimize(self, method="GS", maxiter=20, verbose=False, callback=None, feedback=None,
+                 stat_groups=[], **kw):
+        """_hologram.py:1351-1368 + 1427-1493 with the overrides of _multiplane.py:232-286."""
+        kw.pop("name", None)
+        self._merge_flags(method, feedback, stat_groups, kw)
+        if "GS" not in method:
+            raise ValueError(f"Unsupported optimization method '{method}'")
+        mraf = [h._mraf_setup() for h in self.holograms]
+        for _ in range(maxiter):
+            self._forward()
+            if callback is not None and callback(self):
+                break
+            for h in self.holograms:
+                h._record(h._stat_groups(self.flags["stat_groups"]))
+            for h, m in zip(self.holograms, mraf):
+                h._constrain(m)
+            self._inverse()
+            self.iter += 1
+        self._forward()  # _populate_results: the children refresh their far fields

@@ -54,6 +54,23 @@ def main():
         manifest["cases"][name] = {"oracle_max_abs_diff": worst, "sha256_16": sha,
                                    "keys": sorted(g.keys())}
         print(f"{name:45s} oracle-vs-reference max|d| = {worst:.3e}")
+    from slmsuite.holography.algorithms import MultiplaneHologram as RefMulti
+    for name in cases.MULTI_CASES:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            g = cases.summarize_multi(cases.run_multi_case(name, ref.Hologram, ref.SpotHologram, RefMulti))
+            o = cases.summarize_multi(cases.run_multi_case(name, gs_oracle.OracleHologram, gs_oracle.OracleSpotHologram,
+                                                           gs_oracle.OracleMultiplaneHologram))
+        worst = 0.0
+        for k in g:
+            a, b = np.atleast_1d(np.asarray(g[k], dtype=np.float64)), np.atleast_1d(np.asarray(o[k], dtype=np.float64))
+            worst = max(worst, float(np.max(np.abs(a - b))) if a.shape == b.shape else float("inf"))
+        path = os.path.join(out_dir, name + ".npz")
+        np.savez_compressed(path, **g)
+        sha = hashlib.sha256(open(path, "rb").read()).hexdigest()[:16]
+        manifest["cases"][name] = {"oracle_max_abs_diff": worst, "sha256_16": sha, "keys": sorted(g.keys())}
+        print(f"{name:45s} oracle-vs-reference max|d| = {worst:.3e}")
     with open(os.path.join(out_dir, "MANIFEST.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
 

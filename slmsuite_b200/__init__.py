@@ -9,6 +9,7 @@ Python host classes -> ctypes -> ``libslmgs.so`` (hand-written sm_100a CUDA, C A
 from .hologram import ALGORITHM_DEFAULTS, ALGORITHM_INDEX, FEEDBACK_OPTIONS, Hologram
 from .spots import SpotHologram
 from .batch import HologramBatch, optimize_sharded, shard_bounds
+from .multiplane import MultiplaneHologram
 
-__all__ = ["Hologram", "SpotHologram", "HologramBatch", "optimize_sharded", "shard_bounds", "ALGORITHM_DEFAULTS", "ALGORITHM_INDEX", "FEEDBACK_OPTIONS"]
+__all__ = ["Hologram", "SpotHologram", "HologramBatch", "MultiplaneHologram", "optimize_sharded", "shard_bounds", "ALGORITHM_DEFAULTS", "ALGORITHM_INDEX", "FEEDBACK_OPTIONS"]
 __version__ = "0.1.0"

@@ -126,6 +126,8 @@ struct slmgs_ctx {
     bool ff_valid;     // farfield / amp_ff hold the transform of the current phase (stepped mode)
     double fnorm;      // ||nearfield||_2 == ||farfield||_2 (Parseval, ortho), from the amplitude
     float* phase_saved;
+    cf* mp_sum;        // MultiplaneHologram accumulator, lazily allocated
+    bool own_stream;
     // timing
     bool profiling;
     bool use_pdl;
@@ -285,6 +287,8 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
     c->fnorm = 1.0;
     c->stream = nullptr;
     c->phase_saved = nullptr;
+    c->mp_sum = nullptr;
+    c->own_stream = true;
     c->profiling = false;
     c->use_pdl = env_int("SLMGS_PDL", 1) != 0;
 #ifndef SLMGS_EMULATE
@@ -344,7 +348,7 @@ extern "C" int slmgs_destroy(slmgs_ctx* c) {
     if (c->stream) rt_sync(c->stream);
     void* ptrs[] = {c->fld, c->farfield, c->stage_c, c->stage_f, c->phase, c->amp, c->prop, c->target,
                     c->weights, c->phase_ff, c->amp_ff, c->twA_row, c->twB_row, c->twA_col, c->twB_col, c->acc,
-                    c->partial, c->spot_x, c->spot_y, c->spot_amp, c->spot_pw, c->phase_saved};
+                    c->partial, c->spot_x, c->spot_y, c->spot_amp, c->spot_pw, c->phase_saved, c->mp_sum};
     for (void* p : ptrs)
         if (p) rt_free(p);
 #ifndef SLMGS_EMULATE
@@ -352,7 +356,7 @@ extern "C" int slmgs_destroy(slmgs_ctx* c) {
     if (c->t1) cudaEventDestroy(c->t1);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
 #endif
-    if (c->stream) rt_stream_destroy(c->stream);
+    if (c->stream && c->own_stream) rt_stream_destroy(c->stream);
     delete c;
     return SLMGS_OK;
 }
@@ -596,6 +600,9 @@ static RowArgs row_args(slmgs_ctx* c) {
     a.scale = (float)(1.0 / sqrt((double)c->H * (double)c->W));
     a.H = c->H; a.W = c->W; a.h = c->h; a.w = c->w; a.i0 = c->i0; a.i2 = c->i2;
     a.store_phase = 0;
+    a.mp_sum = nullptr;
+    a.mp_weight = 0.f;
+    a.mp_first = 0;
     a.zero_acc = nullptr;
     a.zero_bs = ACC_N;
     a.pdl = (c->use_pdl && !c->profiling) ? 1 : 0;
@@ -907,6 +914,56 @@ extern "C" int slmgs_constrain_inverse(slmgs_ctx* c, const slmgs_params* p) {
     if ((e = run_row(c, ROW_LAST, ra))) return e;
     c->ff_valid = false;
     return SLMGS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// MultiplaneHologram support
+// ------------------------------------------------------------------------------------------
+extern "C" int slmgs_share_stream(slmgs_ctx* c, slmgs_ctx* leader) {
+    CHECK_CTX(c);
+    if (!leader || leader->device != c->device) return fail(c, SLMGS_ERR_INVALID, "stream leader must live on the same device");
+    if (leader == c) return SLMGS_OK;
+    RT(c, rt_sync(c->stream));
+    if (c->own_stream && c->stream) rt_stream_destroy(c->stream);
+    c->stream = leader->stream;
+    c->own_stream = false;
+    return SLMGS_OK;
+}
+
+extern "C" void* slmgs_nearfield_sum_ptr(slmgs_ctx* c) {
+    if (!c) return nullptr;
+    if (rt_set_device(c->device)) return nullptr;
+    if (!c->mp_sum && dev_alloc(c, &c->mp_sum, (size_t)c->B * c->h * c->w)) return nullptr;
+    return c->mp_sum;
+}
+
+extern "C" int slmgs_constrain_accumulate(slmgs_ctx* c, const slmgs_params* p, float weight, void* sum, int first) {
+    CHECK_CTX(c);
+    int e = check_params(c, p);
+    if (e) return e;
+    if (!sum) return fail(c, SLMGS_ERR_INVALID, "sum is NULL");
+    if (!c->ff_valid || !c->farfield) return fail(c, SLMGS_ERR_STATE, "constrain_accumulate needs a preceding forward()");
+    if ((e = resolve_weights(c))) return e;
+    ColArgs ca = col_args(c);
+    apply_params(ca, p);
+    ca.wgs_update = 0;
+    if ((e = run_col(c, COL_INV, ca))) return e;
+    RowArgs ra = row_args(c);
+    ra.mp_sum = (cf*)sum;
+    ra.mp_weight = weight;
+    ra.mp_first = first ? 1 : 0;
+    if ((e = run_row(c, ROW_LAST, ra))) return e;
+    c->ff_valid = false;
+    return SLMGS_OK;
+}
+
+extern "C" int slmgs_extract_phase_from_sum(slmgs_ctx* c, const void* sum) {
+    CHECK_CTX(c);
+    if (!sum) return fail(c, SLMGS_ERR_INVALID, "sum is NULL");
+    const long long S = (long long)c->h * c->w;
+    ElemArgs a = elem_args(c, sum, c->phase, S);
+    c->ff_valid = false;
+    return launch_elem<EW_ARG_C64>(c, a, c->B);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -164,6 +164,10 @@ struct RowArgs {
     float scale;         // ROW_LAST near-field scale 1/sqrt(H W)
     int H, W, h, w, i0, i2;
     int store_phase;     // ROW_FUSED: also write the phase this iteration
+    cf* mp_sum;          // ROW_LAST, MultiplaneHologram: accumulate weight * nearfield * exp(-i kernel) here instead of
+                         // extracting the phase (_multiplane.py:261-279); [B][h][w], or nullptr
+    float mp_weight;
+    int mp_first;        // first child of the sum: overwrite instead of add
     double* zero_acc;    // accumulator slot to clear for the next column kernel ([B] slots, stride zero_bs), or nullptr
     int zero_bs;
     int pdl;             // launch with programmatic dependent launch
@@ -282,7 +286,18 @@ template <int N, int MODE, bool STORE = false> struct RowKernel {
                 const bool inside = L.active && (full || scu < (unsigned)a.w);
                 const int sc = inside ? (int)scu : 0;
                 const cf z = st.v[u * R + m];
-                if (WRITE) {
+                if (WRITE && !REBUILD && a.mp_sum) {
+                    if (inside) {  // child of a MultiplaneHologram: complex sum over the children, no extraction
+                        cf val = cscale(z, a.scale * a.mp_weight);
+                        if (a.prop) {
+                            float sn, cs;
+                            sincosf(__ldg(a.prop + (long long)L.sr * a.w + sc), &sn, &cs);
+                            val = cmulc(val, cmake(cs, sn));
+                        }
+                        cf* dst = a.mp_sum + (long long)id.by * a.phase_bs + (long long)L.sr * a.w + sc;
+                        *dst = a.mp_first ? val : cadd(*dst, val);
+                    }
+                } else if (WRITE) {
                     if (inside) {
                         float ph = atan2f(z.y, z.x);
                         if (a.prop) ph -= __ldg(a.prop + (long long)L.sr * a.w + sc);

@@ -18,6 +18,7 @@ enum {
     EW_FILL_NAN0 = 7,   // dst = nan_to_num(src, nan=0)                                (reset_weights, :608-614)
     EW_ABS_C64 = 8,     // dst(f32) = |src(c64)|
     EW_PHASE2GRAY = 9,  // dst(u8/u16) = SLM gray level of get_phase() = src + pi (hardware/slms/slm.py:695-743)
+    EW_ARG_C64 = 10,    // dst(f32) = arctan2(src.imag, src.real)   (MultiplaneHologram._nearfield_extract)
 };
 
 struct ElemArgs {
@@ -102,6 +103,9 @@ template <int OP> struct ElemKernel {
             } else if (OP == EW_ABS_C64) {
                 const cf z = srcc[i];
                 dstf[i] = sqrtf(z.x * z.x + z.y * z.y);
+            } else if (OP == EW_ARG_C64) {
+                const cf z = srcc[i];
+                dstf[i] = atan2f(z.y, z.x);
             } else if (OP == EW_PHASE2GRAY) {
                 // get_phase() is float32 (phase + pi, _hologram.py:807-811); SLM.set_phase copies it into a float64
                 // cache, adds the float64 correction, scales, rounds half-to-even, casts, subtracts one and masks.

@@ -23,7 +23,7 @@ def _load(name):
 
 def test_manifest_lists_every_case():
     man = json.load(open(os.path.join(GOLDEN, "MANIFEST.json")))
-    assert set(man["cases"]) == set(cases.CASES)
+    assert set(man["cases"]) == set(cases.CASES) | set(cases.MULTI_CASES)
     # the generator recorded a bit-exact restatement on its NumPy
     assert all(v["oracle_max_abs_diff"] == 0.0 for v in man["cases"].values())
 
@@ -53,6 +53,19 @@ def test_oracle_bit_exact_vs_live_reference(name):
         b = cases.summarize(cases.run_case(name, gs_oracle.OracleHologram, gs_oracle.OracleSpotHologram))
     for k in a:
         np.testing.assert_array_equal(np.asarray(a[k]), np.asarray(b[k]), err_msg=f"{name}:{k}")
+
+
+@pytest.mark.parametrize("name", sorted(cases.MULTI_CASES))
+def test_multiplane_oracle_matches_golden(name):
+    gold = _load(name)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = cases.summarize_multi(cases.run_multi_case(name, gs_oracle.OracleHologram, gs_oracle.OracleSpotHologram,
+                                                         gs_oracle.OracleMultiplaneHologram))
+    assert set(got) == set(gold)
+    for k in gold:
+        np.testing.assert_allclose(np.asarray(got[k], dtype=np.float64), np.asarray(gold[k], dtype=np.float64),
+                                   rtol=2e-4, atol=2e-4, equal_nan=True, err_msg=f"{name}:{k}")
 
 
 def test_crop_bounds_matches_reference_pad_tests():

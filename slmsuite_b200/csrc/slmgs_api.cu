@@ -95,9 +95,16 @@ static int launch_col(int n, int mode, int var, int gx, int gy, int nt, rt_strea
 // ------------------------------------------------------------------------------------------
 enum { ACC_W0 = 0, ACC_W1 = 1, ACC_FNORM = 2, ACC_MEAN = 3, ACC_S0 = 4, ACC_S1 = 5, ACC_S2 = 6, ACC_TMP = 7, ACC_N = 8 };
 
+// a stream may be shared by the child contexts of a MultiplaneHologram: destroyed with its last user
+struct StreamRef {
+    rt_stream s;
+    int refs;
+};
+
 struct slmgs_ctx {
     int device, B, H, W, h, w, i0, i2;
     rt_stream stream;
+    StreamRef* sref;
     std::string err;
     long long launches;
     int sms;
@@ -127,7 +134,6 @@ struct slmgs_ctx {
     double fnorm;      // ||nearfield||_2 == ||farfield||_2 (Parseval, ortho), from the amplitude
     float* phase_saved;
     cf* mp_sum;        // MultiplaneHologram accumulator, lazily allocated
-    bool own_stream;
     // timing
     bool profiling;
     bool use_pdl;
@@ -288,7 +294,7 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
     c->stream = nullptr;
     c->phase_saved = nullptr;
     c->mp_sum = nullptr;
-    c->own_stream = true;
+    c->sref = nullptr;
     c->profiling = false;
     c->use_pdl = env_int("SLMGS_PDL", 1) != 0;
 #ifndef SLMGS_EMULATE
@@ -306,6 +312,7 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
         }                                                          \
     } while (0)
     CR(rt_check(c, rt_stream_create(&c->stream), "stream create"));
+    c->sref = new StreamRef{c->stream, 1};
     const size_t P = (size_t)H * W, S = (size_t)h * w, Bz = (size_t)batch;
     CR(dev_alloc(c, &c->fld, Bz * P));
     CR(dev_alloc(c, &c->phase, Bz * S));
@@ -356,7 +363,14 @@ extern "C" int slmgs_destroy(slmgs_ctx* c) {
     if (c->t1) cudaEventDestroy(c->t1);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
 #endif
-    if (c->stream && c->own_stream) rt_stream_destroy(c->stream);
+    if (c->sref) {
+        if (--c->sref->refs == 0) {
+            rt_stream_destroy(c->sref->s);
+            delete c->sref;
+        }
+    } else if (c->stream) {
+        rt_stream_destroy(c->stream);
+    }
     delete c;
     return SLMGS_OK;
 }
@@ -923,10 +937,15 @@ extern "C" int slmgs_share_stream(slmgs_ctx* c, slmgs_ctx* leader) {
     CHECK_CTX(c);
     if (!leader || leader->device != c->device) return fail(c, SLMGS_ERR_INVALID, "stream leader must live on the same device");
     if (leader == c) return SLMGS_OK;
+    if (c->sref == leader->sref) return SLMGS_OK;
     RT(c, rt_sync(c->stream));
-    if (c->own_stream && c->stream) rt_stream_destroy(c->stream);
+    if (c->sref && --c->sref->refs == 0) {
+        rt_stream_destroy(c->sref->s);
+        delete c->sref;
+    }
+    c->sref = leader->sref;
+    c->sref->refs++;
     c->stream = leader->stream;
-    c->own_stream = false;
     return SLMGS_OK;
 }
 

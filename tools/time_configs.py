@@ -8,7 +8,7 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from slmsuite_b200 import Hologram, HologramBatch, SpotHologram, _lib  # noqa: E402
+from slmsuite_b200 import Hologram, HologramBatch, MultiplaneHologram, SpotHologram, _lib  # noqa: E402
 
 lib = _lib.use_library(os.environ.get("SLMGS_LIB") or _lib.DEFAULT_LIBRARY)
 
@@ -32,7 +32,7 @@ def spots(shape, n, seed):
     return t
 
 
-which = sys.argv[1:] or ["1", "2", "2d", "3", "4", "5"]
+which = sys.argv[1:] or ["1", "2", "2d", "3", "4", "5", "mp", "gray"]
 rng = np.random.default_rng(0)
 if "1" in which:
     h = Hologram(rng.random((512, 512), dtype=np.float32), phase=rng.uniform(-3, 3, (512, 512)).astype(np.float32))
@@ -68,3 +68,30 @@ if "5" in which:
     print(f"config5 ctor {time.time()-t0:.1f} s")
     ms = timed(h, 1, method="WGS-Leonardo", maxiter=20, feedback="computational_spot")
     print(f"config5 SpotHologram 10k spots 8192^2 WGS-Leonardo spot feedback 20 it: {ms:.3f} ms/optimize -> {20/ms*1e3:.0f} it/s")
+if "mp" in which:
+    slm = (1152, 1920)
+    ph = rng.uniform(-3, 3, slm).astype(np.float32)
+    amp = np.ones(slm, np.float32)
+    yy, xx = np.mgrid[-1:1:slm[0] * 1j, -1:1:slm[1] * 1j]
+    kids = [Hologram(spots((4096, 4096), 64, 10 + k), amp=amp, phase=ph, slm_shape=slm,
+                     propagation_kernel=(float(k) * 5 * (xx * xx + yy * yy)).astype(np.float32)) for k in range(2)]
+    m = MultiplaneHologram(kids)
+    m.optimize("WGS-Kim", maxiter=5, verbose=False)
+    lead = kids[0]
+    ms = C.c_float()
+    lib.slmgs_sync(lead._ctx)
+    lib.slmgs_timer_start(lead._ctx)
+    m.optimize("WGS-Kim", maxiter=20, verbose=False)
+    lib.slmgs_timer_stop(lead._ctx, C.byref(ms))
+    print(f"MultiplaneHologram 2 planes, 1152x1920 in 4096^2, WGS-Kim 20 it: {ms.value:.3f} ms -> {20/ms.value*1e3:.0f} it/s")
+if "gray" in which:
+    h = Hologram(spots((4096, 4096), 64, 1), phase=rng.uniform(-3, 3, (1152, 1920)).astype(np.float32), slm_shape=(1152, 1920))
+    h.get_phase_gray(8)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        g = h.get_phase_gray(8)
+    t1 = time.perf_counter()
+    for _ in range(10):
+        p = h.get_phase()
+    t2 = time.perf_counter()
+    print(f"get_phase_gray(8) 1152x1920: {(t1-t0)*100:.3f} ms per call ({g.nbytes/1e6:.1f} MB down) vs get_phase() {(t2-t1)*100:.3f} ms ({p.nbytes/1e6:.1f} MB down)")

@@ -135,6 +135,8 @@ SLMGS_API int slmgs_share_stream(slmgs_ctx* ctx, slmgs_ctx* leader);
 SLMGS_API void* slmgs_nearfield_sum_ptr(slmgs_ctx* ctx);
 SLMGS_API int slmgs_constrain_accumulate(slmgs_ctx*, const slmgs_params*, float weight, void* sum, int first);
 SLMGS_API int slmgs_extract_phase_from_sum(slmgs_ctx*, const void* sum);
+/* one fused iteration of a child (no callback / statistics): row first + fused column kernel + accumulating row inverse */
+SLMGS_API int slmgs_run_accumulate(slmgs_ctx*, const slmgs_params*, float weight, void* sum, int first);
 
 /* ---- statistics ---------------------------------------------------------------------------- */
 /* _calculate_stats(amp_ff, target) pieces, _stats.py:7-116.  out[b][8] =

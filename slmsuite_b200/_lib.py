@@ -86,6 +86,7 @@ SIGNATURES = {
     "slmgs_nearfield_sum_ptr": (C.c_void_p, [_ctx]),
     "slmgs_constrain_accumulate": (C.c_int, [_ctx, _pp, C.c_float, C.c_void_p, C.c_int]),
     "slmgs_extract_phase_from_sum": (C.c_int, [_ctx, C.c_void_p]),
+    "slmgs_run_accumulate": (C.c_int, [_ctx, _pp, C.c_float, C.c_void_p, C.c_int]),
     "slmgs_stats_pixel": (C.c_int, [_ctx, _dp, _dp]),
     "slmgs_window_power": (C.c_int, [_ctx, C.c_int, _ip, _ip, C.c_int, _dp, _dp]),
     "slmgs_save_phase": (C.c_int, [_ctx]),

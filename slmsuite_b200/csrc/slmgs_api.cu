@@ -985,6 +985,56 @@ extern "C" int slmgs_extract_phase_from_sum(slmgs_ctx* c, const void* sum) {
     return launch_elem<EW_ARG_C64>(c, a, c->B);
 }
 
+// One fused iteration of a MultiplaneHologram child (no callback / statistics): row first, the fused column
+// kernel (with the same forward-pass detour as slmgs_run for updates that need |farfield| first), then the row
+// inverse whose epilogue accumulates into `sum`.
+extern "C" int slmgs_run_accumulate(slmgs_ctx* c, const slmgs_params* p, float weight, void* sum, int first) {
+    CHECK_CTX(c);
+    int e = check_params(c, p);
+    if (e) return e;
+    if (!sum) return fail(c, SLMGS_ERR_INVALID, "sum is NULL");
+    if (p->update_weights && p->method == SLMGS_GS) return fail(c, SLMGS_ERR_INVALID, "GS has no weight update");
+    if (p->update_weights && p->feedback == 1 && c->n_spots < 1)
+        return fail(c, SLMGS_ERR_STATE, "spot feedback without slmgs_set_spots");
+    RowArgs ra = row_args(c);
+    if ((e = run_row(c, ROW_FIRST, ra))) return e;
+    ColArgs ca = col_args(c);
+    apply_params(ca, p);
+    // The children's near fields are SUMMED, so the scale of each child's far field matters: the deferred
+    // (one kernel late) weight normalisation of slmgs_run is not allowed here.  Every update goes through the
+    // forward pass + update kernels, which normalise before the constraint.
+    const bool in_kernel = false;
+    const bool need_amp = p->update_weights != 0;
+    const bool need_phase = ca.phase_mode == PHASE_COMPUTE_STORE;
+    if (need_amp || need_phase) {
+        ColArgs fa = col_args(c);
+        fa.store_ampff = need_amp;
+        fa.store_phaseff = need_phase;
+        if ((e = run_col(c, COL_FWD, fa))) return e;
+        if (need_phase) ca.phase_mode = PHASE_STORED;
+    }
+    if (need_amp) {
+        if (p->feedback == 1) e = update_weights_spot_impl(c, p, p->spot_width);
+        else e = update_weights_pixel_impl(c, p);
+        if (e) return e;
+    }
+    ca.wgs_update = in_kernel ? 1 : 0;
+    ca.w_in_slot = c->w_pending;
+    if (ca.wgs_update) {
+        ca.w_out_slot = (c->w_pending == ACC_W0) ? ACC_W1 : ACC_W0;
+        if ((e = zero_slot(c, ca.w_out_slot))) return e;
+    }
+    if ((e = run_col(c, COL_FUSED, ca))) return e;
+    if (ca.wgs_update) c->w_pending = ca.w_out_slot;
+    RowArgs rl = row_args(c);
+    rl.mp_sum = (cf*)sum;
+    rl.mp_weight = weight;
+    rl.mp_first = first ? 1 : 0;
+    if ((e = run_row(c, ROW_LAST, rl))) return e;
+    c->ff_valid = false;
+    return SLMGS_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // statistics
 // ------------------------------------------------------------------------------------------

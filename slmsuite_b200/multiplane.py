@@ -175,6 +175,24 @@ class MultiplaneHologram:
     def optimize_gs(self, iterations, callback):
         """_hologram.py:1427-1493 with _multiplane.py:255-286."""
         mraf = [h._mraf_enabled() for h in self.holograms]
+        if all(h._fusable(callback) for h in self.holograms):
+            # nothing on the host looks at the far fields between the transforms: every child runs one fused
+            # iteration (row first + fused column kernel) whose row inverse accumulates into the shared sum
+            for _ in iterations:
+                first = 1
+                for h, w, m in zip(self.holograms, self.weights, mraf):
+                    h.iter = self.iter
+                    h._update_stats(self.flags["stat_groups"])
+                    params = h._iteration_params(m, stepped=False)
+                    h._check(self._lib.slmgs_run_accumulate(h._ctx, C.byref(params), float(w),
+                                                            C.c_void_p(self._sum), first))
+                    first = 0
+                for h in self.holograms:
+                    h._check(self._lib.slmgs_extract_phase_from_sum(h._ctx, C.c_void_p(self._sum)))
+                self.iter += 1
+            self._forward_children()
+            return
+
         for _ in iterations:
             self._forward_children()  # (A)
             if callback is not None:  # (B.1)

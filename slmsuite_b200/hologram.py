@@ -433,15 +433,42 @@ class Hologram:
         return self._target
 
     def get_farfield(self, shape=None, propagation_kernel=None, affine=None, get=True):
-        """_hologram.py:853-931 for ``shape == self.shape`` and the hologram's own kernel; refreshes
-        ``amp_ff`` like the reference (:900-903).  Other shapes / kernels / affine resampling are
-        outside this path."""
-        if shape is not None and tuple(shape) != tuple(self.shape):
-            raise NotImplementedError("get_farfield(shape != self.shape) is outside the GS/WGS hot path")
-        if propagation_kernel is not None or affine is not None:
-            raise NotImplementedError("get_farfield(propagation_kernel=, affine=) is outside the GS/WGS hot path")
-        ff = self.farfield
-        self._amp_ff_set = True
+        """
+        _hologram.py:853-931: complex DFT far field of the current phase, optionally on a different padded
+        ``shape`` (changes the far-field resolution), with a different ``propagation_kernel`` (other depth), and
+        resampled by an ``affine`` transform ``{"M", "b"}``.  The transform runs on the device (a temporary context
+        for a different shape / kernel); the cubic affine resampling is the same SciPy call
+        the reference's NumPy backend makes.  Like the reference, refreshes ``amp_ff`` when the shape matches.
+        """
+        if shape is None:
+            shape = self.shape
+        if len(shape) == 1:
+            shape = self.slm_shape
+        shape = tuple(int(s) for s in shape)
+        own_kernel = propagation_kernel is None
+        if own_kernel:
+            propagation_kernel = self.propagation_kernel
+        if shape == tuple(self.shape) and own_kernel:
+            ff = self.farfield
+            self._amp_ff_set = True
+        else:
+            if np.isscalar(propagation_kernel) or (propagation_kernel is not None and np.ndim(propagation_kernel) == 0):
+                # "Zeroing can force no kernel to be applied and yield the raw DFT" (:871-873)
+                propagation_kernel = None if float(propagation_kernel) == 0 else np.full(
+                    self.slm_shape, float(propagation_kernel), dtype=self.dtype)
+            if self._batch_size() != 1:
+                raise NotImplementedError("get_farfield(shape=, propagation_kernel=) is per hologram")
+            tmp = Hologram(shape, amp=None if np.isscalar(self._amp) else self._amp, phase=self.phase,
+                           slm_shape=self.slm_shape, propagation_kernel=propagation_kernel, device=self._device)
+            if np.isscalar(self._amp):
+                tmp._check(tmp._lib.slmgs_set_amp_scalar(tmp._ctx, float(self._amp)))
+            ff = tmp.farfield
+            del tmp
+        if affine is not None:
+            from scipy.ndimage import affine_transform as sp_affine_transform
+
+            sp_affine_transform(input=ff, matrix=affine["M"], offset=affine["b"], output_shape=shape, order=3,
+                                output=ff, mode="constant", cval=0)
         return ff
 
     # ------------------------------------------------------------------ optimisation

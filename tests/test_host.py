@@ -236,8 +236,29 @@ def test_set_target_renormalises_and_farfield_accessor(emu):
     # uniform amplitude, zero phase -> all the power in the centre pixel of the centred far field
     assert np.isclose(abs(ff[32, 32]), 1, rtol=1e-5) and np.isclose(np.sum(np.abs(ff) ** 2), 1, rtol=1e-5)
     assert np.allclose(h.amp_ff, np.abs(ff), atol=1e-7)
-    with pytest.raises(NotImplementedError):
-        h.get_farfield(shape=(128, 128))
+    # other padded shape / other depth (reference get_farfield(shape=, propagation_kernel=), _hologram.py:853-931)
+    from oracle import gs_oracle
+
+    rng = np.random.default_rng(12)
+    ph = rng.uniform(-3, 3, (40, 56)).astype(np.float32)
+    amp = (1 + rng.random((40, 56))).astype(np.float32)
+    kern = rng.uniform(-2, 2, (40, 56)).astype(np.float32)
+    g = Hologram((64, 64), amp=amp, phase=ph, slm_shape=(40, 56))
+    o = gs_oracle.OracleHologram((128, 256), amp=amp, phase=ph, slm_shape=(40, 56), propagation_kernel=kern)
+    o._forward()
+    got = g.get_farfield(shape=(128, 256), propagation_kernel=kern)
+    assert got.shape == (128, 256) and np.linalg.norm(got - o.farfield) / np.linalg.norm(o.farfield) < 1e-5
+    o2 = gs_oracle.OracleHologram((128, 128), amp=amp, phase=ph, slm_shape=(40, 56))
+    o2._forward()
+    assert np.linalg.norm(g.get_farfield(shape=(128, 128)) - o2.farfield) / np.linalg.norm(o2.farfield) < 1e-5
+    from scipy.ndimage import affine_transform
+
+    aff = {"M": np.array([[1.1, 0.05], [-0.02, 0.9]]), "b": np.array([3.0, -2.0])}
+    want = affine_transform(o2.farfield, aff["M"], offset=aff["b"], output_shape=(128, 128), order=3, mode="constant", cval=0)
+    got = g.get_farfield(shape=(128, 128), affine=aff)
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-4
+    with pytest.raises(ValueError, match="powers of two"):
+        g.get_farfield(shape=(100, 128))
     with pytest.raises(ValueError, match="does not match hologram shape"):
         h.set_target(np.zeros((32, 32), np.float32))
 

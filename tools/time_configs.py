@@ -32,7 +32,7 @@ def spots(shape, n, seed):
     return t
 
 
-which = sys.argv[1:] or ["1", "2", "2d", "3", "4", "5", "mp", "gray"]
+which = sys.argv[1:] or ["1", "2", "2d", "3", "4", "5", "mp", "gray", "refbench"]
 rng = np.random.default_rng(0)
 if "1" in which:
     h = Hologram(rng.random((512, 512), dtype=np.float32), phase=rng.uniform(-3, 3, (512, 512)).astype(np.float32))
@@ -95,3 +95,9 @@ if "gray" in which:
         p = h.get_phase()
     t2 = time.perf_counter()
     print(f"get_phase_gray(8) 1152x1920: {(t1-t0)*100:.3f} ms per call ({g.nbytes/1e6:.1f} MB down) vs get_phase() {(t2-t1)*100:.3f} ms ({p.nbytes/1e6:.1f} MB down)")
+if "refbench" in which:
+    # the reference's own benchmark: tests/holography/test_algorithms.py:121-145 (1024^2, 20 spots, 20 iterations)
+    for method in ("GS", "WGS-Leonardo", "WGS-Kim", "WGS-Nogrette"):
+        h = Hologram(spots((1024, 1024), 20, 7), phase=rng.uniform(-3, 3, (1024, 1024)).astype(np.float32))
+        ms = timed(h, 5, method=method, maxiter=20)
+        print(f"reference benchmark test_gs_speed[{method}] 1024^2 20 it: {ms:.3f} ms/optimize -> {20/ms*1e3:.0f} it/s")

@@ -174,22 +174,9 @@ template <class T> static int dev_alloc(slmgs_ctx* c, T** p, size_t count) {
 }
 
 static void make_twiddles(int n, std::vector<cf>& a, std::vector<cf>& b) {
-    LaunchInfo li = size_info(n);
-    (void)li;
-    // radices: recover from the plan through the instantiated sizes (R0 = N / M1)
-    int r0, r1, r2;
-    switch (n) {
-        case 16: r0 = 16; r1 = 1; r2 = 1; break;
-        case 32: r0 = 2; r1 = 16; r2 = 1; break;
-        case 64: r0 = 4; r1 = 16; r2 = 1; break;
-        case 128: r0 = 8; r1 = 16; r2 = 1; break;
-        case 256: r0 = 16; r1 = 16; r2 = 1; break;
-        case 512: r0 = 2; r1 = 16; r2 = 16; break;
-        case 1024: r0 = 4; r1 = 16; r2 = 16; break;
-        case 2048: r0 = 8; r1 = 16; r2 = 16; break;
-        case 4096: r0 = 16; r1 = 16; r2 = 16; break;
-        default: r0 = 32; r1 = 16; r2 = 16; break;
-    }
+    // twA[k0*M1 + j] = exp(-2 pi i j k0 / N), twB[k1*R2 + n2] = exp(-2 pi i n2 k1 / M1) for the plan of this size
+    const LaunchInfo li = size_info(n);
+    const int r0 = li.r0, r1 = li.r1, r2 = li.r2;
     const int m1 = r1 * r2;
     a.resize(n);
     b.resize(m1);

@@ -16,6 +16,7 @@ struct LaunchInfo {
     int maxt;    // max threads per block
     int padn;    // padded line length (complex elements)
     int ns;      // number of radix stages
+    int r0, r1, r2;  // stage radices of the plan (twiddle table layout)
 };
 
 #define SLMGS_DECL(N_)                                                                                        \

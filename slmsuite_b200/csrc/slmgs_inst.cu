@@ -80,6 +80,9 @@ LaunchInfo SLMGS_CAT(launch_info_, SLMGS_N)() {
     i.maxt = 16384 / F::E;
     i.padn = F::PADN;
     i.ns = F::NS;
+    i.r0 = F::R0;
+    i.r1 = F::R1;
+    i.r2 = F::R2;
     return i;
 }
 

@@ -71,6 +71,8 @@ typedef struct {
     float mraf_factor;
     int feedback;           /* 0: pixel feedback ("computational"); 1: per-spot window feedback ("computational_spot") */
     int spot_width;         /* spot_integration_width_knm, _spots.py:1292-1297 (feedback == 1) */
+    int zero_weights;       /* MRAF zero-region accumulator in use (hasattr(self, "zero_weights")), _hologram.py:1511-1515 */
+    float zero_factor;      /* flags.get("zero_factor", 1), :1615 */
 } slmgs_params;
 
 SLMGS_API int slmgs_version(void);

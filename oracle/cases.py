@@ -141,6 +141,18 @@ def _c(H, S):
             dict(method="WGS-Leonardo", maxiter=6, mraf_factor=0.7))
 
 
+@case("mraf_zero_factor_gs_64")
+def _c(H, S):  # zero-region accumulator, _hologram.py:1511-1515, :1613-1616
+    return (H(target=_mraf_target(), phase=_phase(27, (64, 64))),
+            dict(method="GS", maxiter=10, zero_factor=0.5))
+
+
+@case("mraf_zero_factor_kim_64")
+def _c(H, S):
+    return (H(target=_mraf_target(), phase=_phase(28, (64, 64))),
+            dict(method="WGS-Kim", maxiter=9, zero_factor=0.25, mraf_factor=0.8, fix_phase_iteration=4))
+
+
 # ---- SpotHologram -----------------------------------------------------------------------
 @case("spot_rect_64_leonardo_spotfb")
 def _c(H, S):

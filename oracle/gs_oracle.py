@@ -293,6 +293,8 @@ class OracleHologram:
     def reset_weights(self):
         """_hologram.py:603-614."""
         self.weights = self.target.copy()
+        if hasattr(self, "zero_weights"):
+            self.zero_weights *= 0
         np.nan_to_num(self.weights, copy=False, nan=0)
 
     def reset(self, reset_phase=True):
@@ -416,6 +418,10 @@ class OracleHologram:
             return None
         noise = np.isnan(self.target)
         zero = np.abs(self.target) == 0
+        # complex accumulator over the zero region, created once and then always used (:1511-1515)
+        if "zero_factor" in self.flags and self.flags["zero_factor"] != 0:
+            if int(np.sum(zero)) > 0 and not hasattr(self, "zero_weights"):
+                self.zero_weights = np.zeros((int(np.sum(zero)),), dtype=self.dtype_complex)
         signal = np.logical_not(np.logical_or(noise, zero))
         return {"noise": noise, "zero": zero, "signal": signal}
 
@@ -448,7 +454,12 @@ class OracleHologram:
             np.exp(1j * self.phase_ff, out=self.farfield)
             np.multiply(self.farfield, self.weights, out=self.farfield)
         else:
-            self.farfield[mraf["zero"]] = 0
+            if hasattr(self, "zero_weights"):  # :1613-1616
+                fz = self.farfield[mraf["zero"]]
+                self.zero_weights -= fl.get("zero_factor", 1) * np.abs(fz) * fz
+                self.farfield[mraf["zero"]] = self.zero_weights
+            else:
+                self.farfield[mraf["zero"]] = 0
             if not fl.get("fixed_phase", False):
                 self.phase_ff = np.arctan2(self.farfield.imag, self.farfield.real, out=self.phase_ff)
             np.exp(1j * self.phase_ff, where=mraf["signal"], out=self.farfield)

@@ -42,6 +42,8 @@ class Params(C.Structure):
         ("mraf_factor", C.c_float),
         ("feedback", C.c_int),
         ("spot_width", C.c_int),
+        ("zero_weights", C.c_int),
+        ("zero_factor", C.c_float),
     ]
 
 

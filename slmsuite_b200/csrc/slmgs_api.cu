@@ -134,6 +134,7 @@ struct slmgs_ctx {
     double fnorm;      // ||nearfield||_2 == ||farfield||_2 (Parseval, ortho), from the amplitude
     float* phase_saved;
     cf* mp_sum;        // MultiplaneHologram accumulator, lazily allocated
+    cf* zero_w;        // MRAF zero-region accumulator image, lazily allocated
     // timing
     bool profiling;
     bool use_pdl;
@@ -281,6 +282,7 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
     c->stream = nullptr;
     c->phase_saved = nullptr;
     c->mp_sum = nullptr;
+    c->zero_w = nullptr;
     c->sref = nullptr;
     c->profiling = false;
     c->use_pdl = env_int("SLMGS_PDL", 1) != 0;
@@ -342,7 +344,7 @@ extern "C" int slmgs_destroy(slmgs_ctx* c) {
     if (c->stream) rt_sync(c->stream);
     void* ptrs[] = {c->fld, c->farfield, c->stage_c, c->stage_f, c->phase, c->amp, c->prop, c->target,
                     c->weights, c->phase_ff, c->amp_ff, c->twA_row, c->twB_row, c->twA_col, c->twB_col, c->acc,
-                    c->partial, c->spot_x, c->spot_y, c->spot_amp, c->spot_pw, c->phase_saved, c->mp_sum};
+                    c->partial, c->spot_x, c->spot_y, c->spot_amp, c->spot_pw, c->phase_saved, c->mp_sum, c->zero_w};
     for (void* p : ptrs)
         if (p) rt_free(p);
 #ifndef SLMGS_EMULATE
@@ -520,6 +522,7 @@ extern "C" int slmgs_reset_weights(slmgs_ctx* c) {
     ElemArgs a = elem_args(c, c->target, c->weights, P);
     a.src_bs = c->target_shared ? 0 : P;
     c->w_pending = -1;
+    if (c->zero_w) RT(c, rt_memset(c->zero_w, 0, (size_t)c->B * P * sizeof(cf), c->stream));  // zero_weights *= 0, :609-610
     return launch_elem<EW_FILL_NAN0>(c, a, c->B);
 }
 extern "C" int slmgs_set_weights(slmgs_ctx* c, const float* weights) {
@@ -633,6 +636,8 @@ static ColArgs col_args(slmgs_ctx* c) {
     a.wgs.p = 0.f; a.wgs.f = 0.f;
     a.wgs.inv_fnorm = (float)(1.0 / c->fnorm);
     a.wgs.neg_inv_mean = -1.0f;
+    a.zero_w = c->zero_w;
+    a.zero_factor = 1.0f;
     a.pdl = (c->use_pdl && !c->profiling) ? 1 : 0;
     return a;
 }
@@ -678,6 +683,8 @@ static int ensure_farfield(slmgs_ctx* c) {
     return dev_alloc(c, &c->farfield, (size_t)c->B * c->H * c->W);
 }
 static void apply_params(ColArgs& a, const slmgs_params* p) {
+    a.zero_factor = p->zero_factor;
+    if (!(p->mraf && p->zero_weights)) a.zero_w = nullptr;
     a.wgs.method = p->method;
     a.wgs.p = p->feedback_exponent;
     a.wgs.f = p->feedback_factor;
@@ -686,8 +693,20 @@ static void apply_params(ColArgs& a, const slmgs_params* p) {
     a.mraf_has_factor = p->mraf_has_factor;
     a.mraf_factor = p->mraf_factor;
 }
+static int ensure_zero_weights(slmgs_ctx* c) {
+    if (c->zero_w) return 0;
+    const size_t n = (size_t)c->B * c->H * c->W;
+    int e = dev_alloc(c, &c->zero_w, n);
+    if (e) return e;
+    return rt_check(c, rt_memset(c->zero_w, 0, n * sizeof(cf), c->stream), "memset");
+}
+
 static int check_params(slmgs_ctx* c, const slmgs_params* p) {
     if (!p) return fail(c, SLMGS_ERR_INVALID, "params is NULL");
+    if (p->mraf && p->zero_weights) {
+        int e = ensure_zero_weights(c);
+        if (e) return e;
+    }
     if (p->method < SLMGS_GS || p->method > SLMGS_WGS_TANH) return fail(c, SLMGS_ERR_INVALID, "unknown method");
     if (p->phase_mode < 0 || p->phase_mode > 2) return fail(c, SLMGS_ERR_INVALID, "unknown phase_mode");
     return 0;

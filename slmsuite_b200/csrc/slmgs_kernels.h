@@ -386,6 +386,8 @@ struct ColArgs {
     int mraf;             // target carries NaN noise region (_hologram.py:1495-1548)
     int mraf_has_factor;
     float mraf_factor;
+    cf* zero_w;           // MRAF zero-region accumulator image ([B][H][W], tile-major), or nullptr (_hologram.py:1613-1616)
+    float zero_factor;
     int store_ampff, store_phaseff, store_farfield;  // COL_FWD outputs
     int pdl;              // launch with programmatic dependent launch
 };
@@ -558,6 +560,14 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
                 if (mraf) {
                     if (zero_region) {
                         g = cmake(0.f, 0.f);
+                        if (a.zero_w) {  // zero_weights -= zero_factor * |F| * F; farfield[zero] = zero_weights
+                            const cf fz = cscale(z, fscale);
+                            const float k = a.zero_factor * sqrtf(fz.x * fz.x + fz.y * fz.y);
+                            cf zw = a.zero_w[L.ibase + off];
+                            zw = cmake(zw.x - k * fz.x, zw.y - k * fz.y);
+                            a.zero_w[L.ibase + off] = zw;
+                            g = zw;
+                        }
                     } else if (t != t) {  // noise region keeps the (scaled) field (:1643-1653)
                         const float q = a.mraf_has_factor ? fscale * a.mraf_factor : fscale;
                         g = cscale(z, q);

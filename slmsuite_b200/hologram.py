@@ -198,6 +198,7 @@ class Hologram:
         self.flags = kwargs
         self._target = None
         self._mraf_cache = None
+        self._zero_weights_active = False
         self._set_target(target, reset_weights=False)
 
         self._phase_set = False
@@ -533,6 +534,14 @@ class Hologram:
                 self._mraf_cache = bool(np.isnan(np.sum(self._target)))
         return self._mraf_cache
 
+    def _zero_weights_on(self, mraf):
+        """The MRAF zero-region accumulator exists once ``zero_factor`` was non-zero with a non-empty zero region and is
+        used from then on (``hasattr(self, "zero_weights")``, _hologram.py:1511-1515, :1613-1616)."""
+        if mraf and not self._zero_weights_active and self.flags.get("zero_factor", 0) != 0:
+            with np.errstate(invalid="ignore"):
+                self._zero_weights_active = bool(np.any(self._target == 0))
+        return mraf and self._zero_weights_active
+
     def _fusable(self, callback):
         """
         The fused launch sequence (``slmgs_run``) is legal when nothing on the host needs the far field
@@ -608,6 +617,8 @@ class Hologram:
             mraf_factor=float(mf if mf is not None else 1.0),
             feedback=self._feedback_params()[0],
             spot_width=self._feedback_params()[1],
+            zero_weights=int(self._zero_weights_on(mraf)),
+            zero_factor=float(fl.get("zero_factor", 1)),
         )
 
     def optimize_gs(self, iterations, callback):

@@ -50,7 +50,8 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
 
 
 def test_params_struct_layout_matches_header():
-    # slmgs_params: 3 ints, 2 floats, 2 ints, 1 float, 2 ints -> 40 bytes, no padding
-    assert ctypes.sizeof(_lib.Params) == 40
+    # slmgs_params: 3 ints, 2 floats, 2 ints, 1 float, 3 ints, 1 float -> 48 bytes, no padding
+    assert ctypes.sizeof(_lib.Params) == 48
+    assert _lib.Params.zero_factor.offset == 44
     assert _lib.Params.mraf_factor.offset == 28
     assert _lib.Params.spot_width.offset == 36

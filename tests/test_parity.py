@@ -118,6 +118,30 @@ def test_spot_feedback_fused_sequence_vs_oracle(backend):
     assert a.flags["fixed_phase"] == b.flags["fixed_phase"] is True
 
 
+def test_kim_fix_phase_efficiency_vs_oracle(backend):
+    """WGS-Kim fixing on an efficiency threshold (_hologram.py:1559-1572) needs per-iteration statistics: stepped path."""
+    from oracle import gs_oracle
+    from slmsuite_b200 import Hologram
+
+    rng = np.random.default_rng(51)
+    target = np.zeros((64, 64), dtype=np.float32)
+    target[rng.integers(0, 64, 12), rng.integers(0, 64, 12)] = 1
+    phase = rng.uniform(-np.pi, np.pi, (64, 64)).astype(np.float32)
+    kw = dict(method="WGS-Kim", maxiter=12, verbose=False, stat_groups=["computational"], fix_phase_efficiency=0.5,
+              fix_phase_iteration=100)
+    a = Hologram(target, phase=phase)
+    a.optimize(**kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        b = gs_oracle.OracleHologram(target, phase=phase)
+        b.optimize(**kw)
+    assert a.flags["fixed_phase"] == b.flags["fixed_phase"] is True
+    assert a.stats["flags"]["fixed_phase"] == b.stats["flags"]["fixed_phase"]
+    assert rel_rmse(a.amp_ff, b.amp_ff) <= 1e-5
+    assert rel_rmse(a.weights, b.weights) <= 1e-5
+    assert rel_rmse(a.stats["stats"]["computational"]["efficiency"], b.stats["stats"]["computational"]["efficiency"]) <= 1e-4
+
+
 def test_oracle_side_by_side_seeded(backend):
     """Product vs the oracle restatement on a case that is not in the golden set."""
     from oracle import gs_oracle

@@ -138,6 +138,7 @@ struct slmgs_ctx {
     // timing
     bool profiling;
     bool use_pdl;
+    bool prefetch;
 #ifndef SLMGS_EMULATE
     cudaEvent_t t0, t1;
     std::vector<cudaEvent_t> ev_pool;   // pairs
@@ -286,6 +287,8 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
     c->sref = nullptr;
     c->profiling = false;
     c->use_pdl = env_int("SLMGS_PDL", 1) != 0;
+    // L2 prefetch of the next tile's field rows: +2.4 % on dense 4096^2, -0.4 % on zero-padded problems
+    c->prefetch = env_int("SLMGS_PREFETCH", (h == H) ? 1 : 0) != 0;
 #ifndef SLMGS_EMULATE
     c->t0 = c->t1 = nullptr;
     c->ev_used = 0;
@@ -610,6 +613,7 @@ static RowArgs row_args(slmgs_ctx* c) {
     a.zero_acc = nullptr;
     a.zero_bs = ACC_N;
     a.pdl = (c->use_pdl && !c->profiling) ? 1 : 0;
+    a.pf_dist = c->prefetch ? c->sms * (c->row_threads <= 512 ? 2 : 1) : 0;
     return a;
 }
 static ColArgs col_args(slmgs_ctx* c) {
@@ -639,6 +643,7 @@ static ColArgs col_args(slmgs_ctx* c) {
     a.zero_w = c->zero_w;
     a.zero_factor = 1.0f;
     a.pdl = (c->use_pdl && !c->profiling) ? 1 : 0;
+    a.pf_dist = c->prefetch ? c->sms * (c->col_threads <= 512 ? 2 : 1) : 0;
     return a;
 }
 // profiling: bracket a launch with events from a pool (class k: 0..2 row modes, 3..5 column modes)

@@ -171,6 +171,7 @@ struct RowArgs {
     double* zero_acc;    // accumulator slot to clear for the next column kernel ([B] slots, stride zero_bs), or nullptr
     int zero_bs;
     int pdl;             // launch with programmatic dependent launch
+    int pf_dist;         // L2 prefetch distance in tiles (blocks resident on the GPU), 0 = off
 };
 
 // STORE (ROW_FUSED only): this launch also writes the phase (last iteration of a fused run)
@@ -324,6 +325,16 @@ template <int N, int MODE, bool STORE = false> struct RowKernel {
         const Loc L = locate(a, smem, id);
         if constexpr (P == 0) {
             if (a.zero_acc && id.bx == 0 && id.tid == 0) a.zero_acc[(long long)id.by * a.zero_bs] = 0.0;
+            if (MODE != ROW_FIRST && a.pf_dist > 0) {
+                // pull the rows of the tile this SM will run next into L2 while this tile computes
+                const int lines = id.nthreads / F::TPL;
+                const int nsr = (id.bx + a.pf_dist) * lines + id.tid / F::TPL;
+                if (nsr < a.h) {
+                    const int nfr = (nsr + a.i0 + (a.H >> 1)) & (a.H - 1);
+                    const char* base = reinterpret_cast<const char*>(a.fld + (long long)id.by * a.fld_bs + (long long)nfr * a.W);
+                    for (int i = id.tid % F::TPL; i < (int)(N * sizeof(cf) / 128); i += F::TPL) prefetch_l2(base + (size_t)i * 128);
+                }
+            }
         }
         if constexpr (MODE == ROW_FIRST) {
             if constexpr (P == 0) build_nearfield(st, a, id, L);
@@ -390,6 +401,7 @@ struct ColArgs {
     float zero_factor;
     int store_ampff, store_phaseff, store_farfield;  // COL_FWD outputs
     int pdl;              // launch with programmatic dependent launch
+    int pf_dist;          // L2 prefetch distance in tiles (blocks resident on the GPU), 0 = off
 };
 
 // CT: columns per tile known at compile time (block of MAXT threads), 0 = derived from blockDim at run time
@@ -593,7 +605,20 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
             F::template inv_stage<NS - 1 - P>(st.v, L.lt, a.twA, a.twB, L.s, L.C);
             if constexpr (P == NS - 1) store_rows(st, a, L);
         } else {
-            if constexpr (P == 0) load_rows(st, a, L);
+            if constexpr (P == 0) {
+                load_rows(st, a, L);
+                if (a.pf_dist > 0 && a.h == a.H) {
+                    // dense field: pull the rows of the tile group this SM will run next into L2 (a 128-byte line
+                    // holds 16 columns = several tiles, so one tile of each line-sharing group issues the prefetch)
+                    const int per_line = 16 / L.C > 0 ? 16 / L.C : 1;
+                    const int nb = id.bx + a.pf_dist;
+                    if ((id.bx % per_line) == 0 && nb < id.gx && L.col == 0) {
+                        const cf* base = a.fld + (long long)id.by * a.fld_bs + (long long)nb * L.C;
+                        SLMGS_UNROLL
+                        for (int m = 0; m < E; ++m) prefetch_l2(base + (long long)(L.lt + F::TPL * m) * a.W);
+                    }
+                }
+            }
             if constexpr (P < NS - 1) {
                 F::template fwd_stage<P>(st.v, L.lt, a.twA, a.twB, L.s, L.C);
             } else if constexpr (P == NS - 1) {

@@ -36,8 +36,7 @@ phase = rng.uniform(-np.pi, np.pi, slm).astype(np.float32)
 h = Hologram(target, phase=phase, slm_shape=slm)
 kw = {"fix_phase_iteration": a.fix} if a.method == "WGS-Kim" else {}
 h.optimize(a.method, maxiter=a.iters, verbose=False, **kw)
-g = (4 * 4)
-geo = (np.zeros(4, dtype=np.int32))
+geo = np.zeros(4, dtype=np.int32)
 h._lib.slmgs_launch_geometry(h._ctx, _lib.iptr(geo))
 print("done", a.method, shape, slm, "launches", h._lib.slmgs_launch_count(h._ctx), "geometry", geo.tolist(),
       "amp_ff max", float(h.amp_ff.max()))

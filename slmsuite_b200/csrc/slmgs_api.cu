@@ -600,7 +600,6 @@ static RowArgs row_args(slmgs_ctx* c) {
     a.amp = c->amp;
     a.amp_bs = c->amp_per_hologram ? (long long)c->h * c->w : 0;
     a.prop = c->prop;
-    a.nearfield = nullptr;
     a.twA = c->twA_row;
     a.twB = c->twB_row;
     a.amp_scalar = c->amp_scalar;

@@ -157,11 +157,10 @@ struct RowArgs {
     const float* amp;    // [h][w] (or [B][h][w]) source amplitude, or nullptr -> amp_scalar
     long long amp_bs;
     const float* prop;   // [h][w] propagation kernel or nullptr (shared by the batch)
-    cf* nearfield;       // ROW_LAST only: optional [B][h][w] complex near-field crop (scaled), or nullptr
     const cf* twA;       // twiddle tables for N = W
     const cf* twB;
     float amp_scalar;
-    float scale;         // ROW_LAST near-field scale 1/sqrt(H W)
+    float scale;         // ortho scale 1/sqrt(H W) of the inverse transform (MultiplaneHologram sum)
     int H, W, h, w, i0, i2;
     int store_phase;     // ROW_FUSED: also write the phase this iteration
     cf* mp_sum;          // ROW_LAST, MultiplaneHologram: accumulate weight * nearfield * exp(-i kernel) here instead of
@@ -303,8 +302,6 @@ template <int N, int MODE, bool STORE = false> struct RowKernel {
                         float ph = atan2f(z.y, z.x);
                         if (a.prop) ph -= __ldg(a.prop + (long long)L.sr * a.w + sc);
                         a.phase[L.pbase + sc] = ph;
-                        if (!REBUILD && a.nearfield)
-                            a.nearfield[(long long)id.by * a.phase_bs + (long long)L.sr * a.w + sc] = cscale(z, a.scale);
                     }
                 }
                 cf val = cmake(0.f, 0.f);

@@ -37,6 +37,13 @@ def _build_emu():
     subprocess.run(["make", "-s", "-j8", "-C", CSRC, "emu"], check=True)
 
 
+def _build_cuda():
+    """libslmgs.so is a build artefact (git-ignored): build it when a fresh checkout has none."""
+    if os.path.exists(CUDA_LIB):
+        return
+    subprocess.run(["make", "-s", "-j8", "-C", CSRC], check=True)
+
+
 def gpu_present():
     return os.path.exists("/dev/nvidiactl") or os.path.exists("/dev/nvidia0")
 
@@ -45,6 +52,12 @@ def gpu_present():
 def emu_library():
     _build_emu()
     return EMU_LIB
+
+
+@pytest.fixture(scope="session")
+def cuda_library():
+    _build_cuda()
+    return CUDA_LIB
 
 
 @pytest.fixture(params=["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
@@ -57,6 +70,7 @@ def backend(request, emu_library):
     else:
         if not gpu_present():
             pytest.skip("no CUDA device")
+        _build_cuda()
         _lib.use_library(CUDA_LIB)
     return request.param
 
@@ -75,5 +89,6 @@ def cuda():
 
     if not gpu_present():
         pytest.skip("no CUDA device")
+    _build_cuda()
     _lib.use_library(CUDA_LIB)
     return "cuda"

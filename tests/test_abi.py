@@ -26,10 +26,8 @@ def test_bindings_cover_the_header():
     assert sorted(_lib.SIGNATURES) == _declared()
 
 
-def test_cuda_library_exports_every_symbol():
-    if not os.path.exists(CUDA_LIB):
-        pytest.fail("slmsuite_b200/libslmgs.so is not built: run __graft_entry__.build()")
-    lib = ctypes.CDLL(CUDA_LIB)
+def test_cuda_library_exports_every_symbol(cuda_library):
+    lib = ctypes.CDLL(cuda_library)
     for name in _declared():
         assert hasattr(lib, name), name
     lib.slmgs_version.restype = ctypes.c_int

@@ -343,11 +343,13 @@ def run_b200(args, rank, local_rank, world):
     hW = SLM_SHAPE[0] * SHAPE[1]
     # model bytes per launch (DESIGN.md "Algorithmic bytes"): column kernel = forward + inverse column pass
     # (4 x 8P) + weights 4P + target 4P + weights write 4P (WGS) [+ phase_ff 4P once Kim has fixed the phase];
-    # averaged over the 50 iterations of this workload: 1 GS-like, 9 WGS, 40 Kim-fixed.
-    col_model = (1 * 36 + 9 * 44 + 40 * 48) / 50.0 * P
+    # averaged over the 50 iterations of this workload: iteration 0 has no update (36 P), iterations 1-8 update with
+    # the phase taken from the field (44 P), iterations 9-49 use the stored phase (48 P; iteration 9 stores it with one
+    # extra forward column pass, counted under col_forward).
+    col_model = (1 * 36 + 8 * 44 + 41 * 48) / 50.0 * P
     row_model = 32.0 * P
     # bytes the implementation must actually move (zero-padding skipped: only the h SLM rows of fld are touched)
-    col_actual = 16.0 * hW + (1 * 4 + 9 * 12 + 40 * 16) / 50.0 * P
+    col_actual = 16.0 * hW + (1 * 4 + 8 * 12 + 41 * 16) / 50.0 * P
     row_actual = 16.0 * hW
     kern = {}
     names = ["row_first", "row_fused", "row_last", "col_forward", "col_fused", "col_inverse"]
@@ -375,7 +377,7 @@ def run_b200(args, rank, local_rank, world):
         "measured": "CUDA events around every launch of the same K steps, repeated right after the timed region "
                     "(event records between kernels disable programmatic dependent launch)",
         "kernels": kern,
-        "iteration_model_frac": (76.0 * 9 + 80.0 * 40 + 68.0) / 50.0 * P * (value / world) / 1e9 / peak,
+        "iteration_model_frac": (68.0 + 76.0 * 8 + 80.0 * 41) / 50.0 * P * (value / world) / 1e9 / peak,
     }
 
     # ---- CPU baseline (oracle port of the reference's NumPy path), bounded sample ------------------

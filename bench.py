@@ -5,11 +5,17 @@ bench.py -- GS iterations/sec at 4096^2 complex64 (BASELINE.json metric).
     python bench.py --gpus N --steps K --warmup W            # this repo (one rank per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path on the host cores
 
-Workload (BASELINE.json configs[1]): Hologram, SLM 1152x1920 zero-padded to 4096x4096, 64-spot
-target, method "WGS-Kim", 50 iterations per optimize().  One STEP = one optimize() of 50 iterations
-from a reset state (first row pass + 50 fused iterations + _populate_results).  N > 1: every rank
-runs its own independent hologram (weak scaling, no collective inside the loop) and the run ends with
-ONE all-gather of the final phases.
+Workload (BASELINE.json configs[1]): Hologram, SLM 1152x1920 zero-padded to 4096x4096, method
+"WGS-Kim", 50 iterations per optimize().  One STEP = one optimize() of 50 iterations from a reset state
+(first row pass + 50 fused iterations + _populate_results).  N > 1: every rank runs its own
+independent hologram (weak scaling, no collective inside the loop) and the run ends with ONE
+all-gather of the final phases.
+
+Target.  SURVEY.md 8d defines two targets for this config: 64 unit spots (parity) and a dense random
+target "for throughput only".  The library skips far-field column tiles whose weights are all zero
+(identical results), which makes throughput depend on the target, so the HEADLINE
+(`value`, `e2e`, `roofline`) is measured on the DENSE target, where every tile is processed -- the
+data-independent worst case -- and the 64-spot target is reported beside it under `sparse_target`.
 
 Timing: CUDA events on the library's own stream (slmgs_timer_*), barrier + synchronise on both
 sides, max over ranks.  The per-iteration working set (fld rows 38 MB + weights/target/phase_ff 192 MB)
@@ -40,12 +46,16 @@ N_SPOTS = 64
 WORKLOAD = "Hologram 1920x1152 SLM padded to 4096x4096, WGS-Kim, 50 iters (BASELINE configs[1])"
 
 
-def make_inputs(seed):
-    """64 unit spots at default_rng(1) positions, seeded explicit phase."""
+def make_inputs(seed, kind="dense"):
+    """dense random target (throughput variant) or 64 unit spots at default_rng(1)
+    positions (parity variant); seeded explicit phase."""
     rng = np.random.default_rng(1)
     pts = rng.integers(0, SHAPE[0], (2, N_SPOTS))
-    target = np.zeros(SHAPE, dtype=np.float32)
-    target[pts[1], pts[0]] = 1
+    if kind == "spots":
+        target = np.zeros(SHAPE, dtype=np.float32)
+        target[pts[1], pts[0]] = 1
+    else:
+        target = rng.random(SHAPE, dtype=np.float32)
     phase = np.random.default_rng(1000 + seed).uniform(-np.pi, np.pi, SLM_SHAPE).astype(np.float32)
     return target, phase
 
@@ -188,54 +198,65 @@ def run_b200(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     lib = _lib.use_library(_lib.DEFAULT_LIBRARY)
-    target, phase0 = make_inputs(rank)
-    holo = Hologram(target, phase=phase0, slm_shape=SLM_SHAPE, device=local_rank)
-    ctx = holo._ctx
-    chk = holo._check
-    chk(lib.slmgs_save_phase(ctx))
-
-    def step_resident():
-        """inputs already in HBM: restore phase + weights on the device, then one optimize()."""
-        chk(lib.slmgs_restore_phase(ctx))
-        holo.reset(reset_phase=False)
-        holo.flags["fixed_phase"] = False
-        holo.optimize(METHOD, maxiter=ITERS, verbose=False)
-
-    # End-to-end path: every step uploads its inputs (normalised target + initial phase) from pinned host
-    # memory through the C ABI, optimises, and downloads the resulting phase.  Two holograms are kept in
-    # flight (ping-pong) so the copies of one step overlap the kernels of the other, the way a caller that
-    # streams holograms through the public API would use it; each context has its own stream.
-    holo_b = Hologram(target, phase=phase0, slm_shape=SLM_SHAPE, device=local_rank)
-    pin_target = torch.from_numpy(np.ascontiguousarray(holo.target)).pin_memory()
-    pin_phase = torch.from_numpy(phase0).pin_memory()
-    pin_out = [torch.empty(SLM_SHAPE, dtype=torch.float32).pin_memory() for _ in range(2)]
     fp = C.POINTER(C.c_float)
-    p_target = C.cast(pin_target.data_ptr(), fp)
-    p_phase = C.cast(pin_phase.data_ptr(), fp)
-    p_out = [C.cast(t.data_ptr(), fp) for t in pin_out]
 
-    def e2e_submit(h):
-        """upload target + phase (host buffers), reset, launch optimize() asynchronously."""
-        h._check(lib.slmgs_set_target(h._ctx, p_target, 0))
-        h._check(lib.slmgs_set_phase(h._ctx, p_phase))
-        h.reset(reset_phase=False)
-        h.flags["fixed_phase"] = False
-        h.optimize(METHOD, maxiter=ITERS, verbose=False)
+    class Workload:
+        """One target variant of the bench config: a device-resident step and an end-to-end step."""
 
-    def e2e_collect(h, slot):
-        h._check(lib.slmgs_get_phase(h._ctx, p_out[slot]))  # D2H, synchronises that hologram's stream
+        def __init__(self, kind):
+            target, phase0 = make_inputs(rank, kind)
+            self.holo = Hologram(target, phase=phase0, slm_shape=SLM_SHAPE, device=local_rank)
+            self.ctx = self.holo._ctx
+            self.holo._check(lib.slmgs_save_phase(self.ctx))
+            # End-to-end path: every step uploads its inputs (normalised target + initial phase) from pinned host
+            # memory through the C ABI, optimises, and downloads the resulting phase.  Two holograms are kept in
+            # flight (ping-pong) so the copies of one step overlap the kernels of the other, the way a caller that
+            # streams holograms through the public API would use it; each context has its own stream.
+            self.holo_b = Hologram(target, phase=phase0, slm_shape=SLM_SHAPE, device=local_rank)
+            self.pin_target = torch.from_numpy(np.ascontiguousarray(self.holo.target)).pin_memory()
+            self.pin_phase = torch.from_numpy(phase0).pin_memory()
+            self.pin_out = [torch.empty(SLM_SHAPE, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self.p_target = C.cast(self.pin_target.data_ptr(), fp)
+            self.p_phase = C.cast(self.pin_phase.data_ptr(), fp)
+            self.p_out = [C.cast(t.data_ptr(), fp) for t in self.pin_out]
 
-    def run_e2e(n_steps):
-        pair = (holo, holo_b)
-        e2e_submit(pair[0])
-        for i in range(n_steps):
-            if i + 1 < n_steps:
-                e2e_submit(pair[(i + 1) % 2])
-            e2e_collect(pair[i % 2], i % 2)
+        def step_resident(self):
+            """inputs already in HBM: restore phase + weights on the device, then one optimize()."""
+            holo = self.holo
+            holo._check(lib.slmgs_restore_phase(self.ctx))
+            holo.reset(reset_phase=False)
+            holo.flags["fixed_phase"] = False
+            holo.optimize(METHOD, maxiter=ITERS, verbose=False)
+
+        def e2e_submit(self, h):
+            """upload target + phase (host buffers), reset, launch optimize() asynchronously."""
+            h._check(lib.slmgs_set_target(h._ctx, self.p_target, 0))
+            h._check(lib.slmgs_set_phase(h._ctx, self.p_phase))
+            h.reset(reset_phase=False)
+            h.flags["fixed_phase"] = False
+            h.optimize(METHOD, maxiter=ITERS, verbose=False)
+
+        def e2e_collect(self, h, slot):
+            h._check(lib.slmgs_get_phase(h._ctx, self.p_out[slot]))  # D2H, synchronises that hologram's stream
+
+        def run_e2e(self, n_steps):
+            pair = (self.holo, self.holo_b)
+            self.e2e_submit(pair[0])
+            for i in range(n_steps):
+                if i + 1 < n_steps:
+                    self.e2e_submit(pair[(i + 1) % 2])
+                self.e2e_collect(pair[i % 2], i % 2)
+
+        def sync(self):
+            self.holo._check(lib.slmgs_sync(self.ctx))
+            self.holo_b._check(lib.slmgs_sync(self.holo_b._ctx))
+
+    wl = Workload("dense")
+    holo, ctx, chk = wl.holo, wl.ctx, wl.holo._check
+    step_resident, run_e2e = wl.step_resident, wl.run_e2e
 
     def barrier():
-        chk(lib.slmgs_sync(ctx))
-        torch.cuda.synchronize()
+        torch.cuda.synchronize()  # device-wide: covers the library's own streams
         if dist is not None:
             dist.barrier()
 
@@ -317,14 +338,46 @@ def run_b200(args, rank, local_rank, world):
     barrier()
     e0 = time.perf_counter()
     run_e2e(args.steps)
-    chk(lib.slmgs_sync(ctx))
-    holo_b._check(lib.slmgs_sync(holo_b._ctx))
+    wl.sync()
     e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - e0))  # host clock: copies are synchronous C-ABI calls
     barrier()
+    dense_info = holo.sparse_info()
+
+    # ---- the 64-spot target of the same config (sparse far field: most column tiles are skipped) --------
+    ws = Workload("spots")
+    for _ in range(3):
+        ws.step_resident()
+    ws.run_e2e(2)
+    ws.sync()
+    barrier()
+    sp_launch0 = lib.slmgs_launch_count(ws.ctx)
+    ws.holo._check(lib.slmgs_timer_start(ws.ctx))
+    for _ in range(args.steps):
+        ws.step_resident()
+    sp_ms = C.c_float()
+    ws.holo._check(lib.slmgs_timer_stop(ws.ctx, C.byref(sp_ms)))
+    sp_launches = lib.slmgs_launch_count(ws.ctx) - sp_launch0
+    sp_total_ms = max_over_ranks(float(sp_ms.value))
+    barrier()
+    e0 = time.perf_counter()
+    ws.run_e2e(args.steps)
+    ws.sync()
+    sp_e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - e0))
+    barrier()
+    sp_info = ws.holo.sparse_info()
 
     iters_total = world * args.steps * ITERS
     value = iters_total / (total_ms * 1e-3)
     e2e_value = iters_total / (e2e_ms * 1e-3)
+    sparse_target = {
+        "target": f"{N_SPOTS} unit spots (SURVEY.md 8d config 2, parity variant)",
+        "value": iters_total / (sp_total_ms * 1e-3), "unit": "it/s", "ms_per_step": sp_total_ms / args.steps,
+        "e2e": {"value": iters_total / (sp_e2e_ms * 1e-3), "unit": "it/s", "ms_per_step": sp_e2e_ms / args.steps},
+        "gpu_launches": int(sp_launches),
+        "sparse_path_used": bool(sp_info[0]), "active_column_tiles": int(sp_info[1]), "column_tiles": int(sp_info[2]),
+        "note": "same config and code path; column tiles whose weights are all zero are skipped (identical results, "
+                "tests/test_sparse.py); not the headline because it depends on the target",
+    }
 
     if rank != 0:
         if dist is not None:
@@ -392,7 +445,9 @@ def run_b200(args, rank, local_rank, world):
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "c64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "method": METHOD, "iters_per_step": ITERS, "shape": list(SHAPE),
-                   "slm_shape": list(SLM_SHAPE), "n_spots": N_SPOTS, "parallelism": f"replicas x{world}",
+                   "slm_shape": list(SLM_SHAPE), "parallelism": f"replicas x{world}",
+                   "target": "dense random (SURVEY.md 8d config 2 throughput variant): every far-field column tile "
+                             f"is processed ({dense_info[1]}/{dense_info[2]} active, sparse path used: {bool(dense_info[0])})",
                    "l2": "working set 230 MB/iteration > 126 MB L2, no flush needed",
                    "final_allgather_ms": ag_ms},
         "clocks": clocks,
@@ -404,6 +459,7 @@ def run_b200(args, rank, local_rank, world):
         "host_submit_ms_per_step": 1e3 * host_s / args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "sparse_target": sparse_target,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:

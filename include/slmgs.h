@@ -119,6 +119,16 @@ SLMGS_API int slmgs_get_phase_gray(slmgs_ctx*, int bitdepth, const double* corre
  * the fused kernels.  Callbacks and per-iteration statistics go through the stepped entry points. */
 SLMGS_API int slmgs_run(slmgs_ctx*, const slmgs_params* params, int n_iter, int populate);
 
+/* Sparse far field in slmgs_run (mode 1 = automatic, the default; 0 = always dense).  The constrained far field
+ * weights * exp(i phase_ff) (_hologram.py:1601-1605) is zero wherever weights == 0, so column tiles with all-zero
+ * weights (no MRAF noise pixel, no spot-feedback window) are skipped by the column kernels and their columns are
+ * neither stored nor loaded by the row kernels: identical results, several times faster on spot targets (the
+ * motivation of the reference's CompressedSpotHologram, _spots.py:222-241).  The occupancy is recomputed on the
+ * device after every target / weights upload.  slmgs_sparse_info: out[0] = last slmgs_run was sparse,
+ * out[1] = active column tiles, out[2] = column tiles. */
+SLMGS_API int slmgs_set_sparse(slmgs_ctx*, int mode);
+SLMGS_API int slmgs_sparse_info(const slmgs_ctx*, int* out3);
+
 /* ---- stepped loop (callbacks, statistics, Nogrette, spot feedback, MRAF + WGS) ------------- */
 SLMGS_API int slmgs_forward(slmgs_ctx*);                                   /* _nearfield2farfield + _midloop_cleaning, :1038-1056, :951-959 */
 SLMGS_API int slmgs_update_weights(slmgs_ctx*, const slmgs_params*);       /* Hologram._update_weights, pixel feedback, :1914-1922 -> :1822-1879 */

@@ -78,6 +78,8 @@ SIGNATURES = {
     "slmgs_get_farfield": (C.c_int, [_ctx, _fp]),
     "slmgs_get_phase_gray": (C.c_int, [_ctx, C.c_int, _dp, C.c_void_p]),
     "slmgs_run": (C.c_int, [_ctx, _pp, C.c_int, C.c_int]),
+    "slmgs_set_sparse": (C.c_int, [_ctx, C.c_int]),
+    "slmgs_sparse_info": (C.c_int, [_ctx, _ip]),
     "slmgs_forward": (C.c_int, [_ctx]),
     "slmgs_update_weights": (C.c_int, [_ctx, _pp]),
     "slmgs_set_spots": (C.c_int, [_ctx, C.c_int, _ip, _ip, _fp]),

@@ -135,6 +135,18 @@ struct slmgs_ctx {
     float* phase_saved;
     cf* mp_sum;        // MultiplaneHologram accumulator, lazily allocated
     cf* zero_w;        // MRAF zero-region accumulator image, lazily allocated
+    // sparse far field (fused loop): column tiles whose constrained far field can be non-zero
+    int sparse_mode;               // 0 = off, 1 = automatic
+    bool tiles_dirty;              // weights / target changed since the occupancy flags were computed
+    int* tile_flags;               // device [ntiles]: bit 0 weights != 0, bit 1 target is NaN
+    int* tile_list;                // device [ntiles]: active tiles in order
+    unsigned char* tile_byte;      // device [ntiles]: 1 = active (row kernel filter)
+    std::vector<int> tile_flags_h; // host copy of tile_flags
+    std::vector<int> spot_x_h;     // host copy of the spot x coordinates (window tiles)
+    int tile_key;                  // (mraf, spot width) the device list was built for, -1 = none
+    int n_active;                  // tiles in tile_list
+    bool sparse_now;               // the launches being issued use the tile list
+    bool last_sparse;              // the last slmgs_run used it
     // timing
     bool profiling;
     bool use_pdl;
@@ -284,6 +296,13 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
     c->phase_saved = nullptr;
     c->mp_sum = nullptr;
     c->zero_w = nullptr;
+    c->sparse_mode = env_int("SLMGS_SPARSE", 1) != 0 ? 1 : 0;
+    c->tiles_dirty = true;
+    c->tile_flags = nullptr; c->tile_list = nullptr; c->tile_byte = nullptr;
+    c->tile_key = -1;
+    c->n_active = 0;
+    c->sparse_now = false;
+    c->last_sparse = false;
     c->sref = nullptr;
     c->profiling = false;
     c->use_pdl = env_int("SLMGS_PDL", 1) != 0;
@@ -347,7 +366,8 @@ extern "C" int slmgs_destroy(slmgs_ctx* c) {
     if (c->stream) rt_sync(c->stream);
     void* ptrs[] = {c->fld, c->farfield, c->stage_c, c->stage_f, c->phase, c->amp, c->prop, c->target,
                     c->weights, c->phase_ff, c->amp_ff, c->twA_row, c->twB_row, c->twA_col, c->twB_col, c->acc,
-                    c->partial, c->spot_x, c->spot_y, c->spot_amp, c->spot_pw, c->phase_saved, c->mp_sum, c->zero_w};
+                    c->partial, c->spot_x, c->spot_y, c->spot_amp, c->spot_pw, c->phase_saved, c->mp_sum, c->zero_w,
+                    c->tile_flags, c->tile_list, c->tile_byte};
     for (void* p : ptrs)
         if (p) rt_free(p);
 #ifndef SLMGS_EMULATE
@@ -512,6 +532,7 @@ extern "C" int slmgs_set_target(slmgs_ctx* c, const float* target, int shared) {
     CHECK_CTX(c);
     if (!target) return fail(c, SLMGS_ERR_INVALID, "target is NULL");
     c->target_shared = shared ? 1 : 0;
+    c->tiles_dirty = true;
     return upload_rolled(c, target, c->target, shared ? 1 : c->B);
 }
 extern "C" int slmgs_get_target(slmgs_ctx* c, float* target) {
@@ -525,6 +546,7 @@ extern "C" int slmgs_reset_weights(slmgs_ctx* c) {
     ElemArgs a = elem_args(c, c->target, c->weights, P);
     a.src_bs = c->target_shared ? 0 : P;
     c->w_pending = -1;
+    c->tiles_dirty = true;
     if (c->zero_w) RT(c, rt_memset(c->zero_w, 0, (size_t)c->B * P * sizeof(cf), c->stream));  // zero_weights *= 0, :609-610
     return launch_elem<EW_FILL_NAN0>(c, a, c->B);
 }
@@ -532,6 +554,7 @@ extern "C" int slmgs_set_weights(slmgs_ctx* c, const float* weights) {
     CHECK_CTX(c);
     if (!weights) return fail(c, SLMGS_ERR_INVALID, "weights is NULL");
     c->w_pending = -1;
+    c->tiles_dirty = true;
     return upload_rolled(c, weights, c->weights, c->B);
 }
 extern "C" int slmgs_get_weights(slmgs_ctx* c, float* weights) {
@@ -613,6 +636,12 @@ static RowArgs row_args(slmgs_ctx* c) {
     a.zero_bs = ACC_N;
     a.pdl = (c->use_pdl && !c->profiling) ? 1 : 0;
     a.pf_dist = c->prefetch ? c->sms * (c->row_threads <= 512 ? 2 : 1) : 0;
+    if (c->sparse_now) {
+        a.colflag = c->tile_byte;
+        a.ctile_shift = 0;
+        while ((1 << a.ctile_shift) < c->col_threads / c->icol.tpl) ++a.ctile_shift;
+        a.pf_dist = 0;
+    }
     return a;
 }
 static ColArgs col_args(slmgs_ctx* c) {
@@ -643,6 +672,7 @@ static ColArgs col_args(slmgs_ctx* c) {
     a.zero_factor = 1.0f;
     a.pdl = (c->use_pdl && !c->profiling) ? 1 : 0;
     a.pf_dist = c->prefetch ? c->sms * (c->col_threads <= 512 ? 2 : 1) : 0;
+    if (c->sparse_now) a.tiles = c->tile_list;
     return a;
 }
 // profiling: bracket a launch with events from a pool (class k: 0..2 row modes, 3..5 column modes)
@@ -678,7 +708,8 @@ static int run_col(slmgs_ctx* c, int mode, const ColArgs& a) {
         else if (a.wgs_update && pow_like && a.phase_mode == PHASE_COMPUTE) var = VAR_POW;
         else if (a.wgs_update && pow_like && a.phase_mode == PHASE_STORED) var = VAR_POW_STORED;
     }
-    int e = rt_check(c, launch_col(c->H, mode, var, c->col_gx, c->B, c->col_threads, c->stream, a), "column kernel launch");
+    const int gx = a.tiles ? c->n_active : c->col_gx;
+    int e = rt_check(c, launch_col(c->H, mode, var, gx, c->B, c->col_threads, c->stream, a), "column kernel launch");
     prof_mark(c, 3 + mode, false);
     return e;
 }
@@ -722,8 +753,113 @@ static int check_params(slmgs_ctx* c, const slmgs_params* p) {
 static int update_weights_pixel_impl(slmgs_ctx* c, const slmgs_params* p);
 static int update_weights_spot_impl(slmgs_ctx* c, const slmgs_params* p, int width);
 
+// ------------------------------------------------------------------------------------------
+// Sparse far field.  farfield = weights * exp(i phase_ff) is zero wherever the weights are zero, and a zero
+// weight stays zero under every update, so a column tile with all-zero weights (and no MRAF noise pixel, and no
+// spot-feedback window) contributes nothing: the column kernels launch only the other tiles and the row kernels
+// neither store nor load the skipped columns.  Results are identical to the dense loop; spot targets (the
+// dominant use of the reference, cf. its CompressedSpotHologram rationale, _spots.py:222-241) run several times
+// faster.  Returns with c->sparse_now set when the run should use the tile list.
+// ------------------------------------------------------------------------------------------
+static int prepare_sparse(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
+    c->sparse_now = false;
+    if (!c->sparse_mode || n_iter < 1) return 0;
+    int mraf = 0, spot_width = 0;
+    for (int i = 0; i < n_iter; ++i) {
+        const slmgs_params* p = params + i;
+        if (p->mraf && p->zero_weights) return 0;   // farfield[zero] = zero_weights: dense by construction
+        if (p->update_weights && p->feedback == 0 && (p->mraf || p->method == SLMGS_WGS_NOGRETTE))
+            return 0;                               // pixel updates with a global sum over |farfield| need every tile
+        if (p->mraf) mraf = 1;
+        if (p->update_weights && p->feedback == 1) {
+            if (spot_width && spot_width != p->spot_width) return 0;
+            spot_width = p->spot_width;
+        }
+    }
+    const int C = c->col_threads / c->icol.tpl;
+    const int ntiles = c->W / C;
+    if (ntiles < 4) return 0;
+    int e;
+    if (!c->tile_flags) {
+        if ((e = dev_alloc(c, &c->tile_flags, (size_t)ntiles))) return e;
+        if ((e = dev_alloc(c, &c->tile_list, (size_t)ntiles))) return e;
+        if ((e = dev_alloc(c, &c->tile_byte, (size_t)ntiles))) return e;
+        c->tiles_dirty = true;
+    }
+    if (c->tiles_dirty) {
+        RT(c, rt_memset(c->tile_flags, 0, (size_t)ntiles * sizeof(int), c->stream));
+        TileArgs t;
+        memset(&t, 0, sizeof t);
+        t.weights = c->weights; t.target = c->target;
+        t.img_bs = (long long)c->H * c->W; t.target_bs = c->target_shared ? 0 : t.img_bs;
+        t.tile_elems = (long long)c->H * C;
+        t.flags = c->tile_flags;
+        c->launches++;
+        RT(c, launch_kernel<TileFlagKernel>(ntiles, c->B, 256, 0, c->stream, t));
+        c->tile_flags_h.resize(ntiles);
+        RT(c, rt_d2h(c->tile_flags_h.data(), c->tile_flags, (size_t)ntiles * sizeof(int), c->stream));
+        RT(c, rt_sync(c->stream));
+        c->tiles_dirty = false;
+        c->tile_key = -1;
+    }
+    const int key = mraf | (spot_width << 1);
+    if (key != c->tile_key) {
+        std::vector<unsigned char> on(ntiles, 0);
+        for (int t = 0; t < ntiles; ++t) on[t] = (c->tile_flags_h[t] & (mraf ? 3 : 1)) ? 1 : 0;
+        if (spot_width > 0) {
+            // columns of the analysis.take windows (SpotGatherKernel): x_n + floor(k - (w-1)/2), negative indices wrap
+            const int base = (spot_width & 1) ? -((spot_width - 1) / 2) : -(spot_width / 2);
+            for (int x0 : c->spot_x_h)
+                for (int d = 0; d < spot_width; ++d) {
+                    int x = x0 + base + d;
+                    if (x < 0) x += c->W;
+                    if (x >= c->W) continue;  // out of range: the gather would fault in the reference too
+                    on[((x + (c->W >> 1)) % c->W) / C] = 1;
+                }
+        }
+        std::vector<int> list;
+        for (int t = 0; t < ntiles; ++t)
+            if (on[t]) list.push_back(t);
+        c->n_active = (int)list.size();
+        c->tile_key = key;
+        if (c->n_active > 0) {
+            RT(c, rt_h2d(c->tile_list, list.data(), list.size() * sizeof(int), c->stream));
+            RT(c, rt_h2d(c->tile_byte, on.data(), (size_t)ntiles, c->stream));
+            RT(c, rt_sync(c->stream));  // the host vectors go out of scope
+        }
+    }
+    // worthwhile below half occupancy (the filtered row kernel costs a little more per element than the dense one)
+    c->sparse_now = c->n_active > 0 && 2 * c->n_active <= ntiles;
+    return 0;
+}
+
+extern "C" int slmgs_set_sparse(slmgs_ctx* c, int mode) {
+    CHECK_CTX(c);
+    c->sparse_mode = mode ? 1 : 0;
+    return SLMGS_OK;
+}
+extern "C" int slmgs_sparse_info(const slmgs_ctx* c, int* out3) {
+    if (!c || !out3) return SLMGS_ERR_INVALID;
+    out3[0] = c->last_sparse ? 1 : 0;
+    out3[1] = c->n_active;
+    out3[2] = c->W / (c->col_threads / c->icol.tpl);
+    return SLMGS_OK;
+}
+
+static int run_impl(slmgs_ctx* c, const slmgs_params* params, int n_iter);
+
 extern "C" int slmgs_run(slmgs_ctx* c, const slmgs_params* params, int n_iter, int populate) {
     CHECK_CTX(c);
+    int e = run_impl(c, params, n_iter);
+    c->last_sparse = c->sparse_now;
+    c->sparse_now = false;  // _populate_results and every stepped entry point see the whole far field
+    c->ff_valid = false;
+    if (e) return e;
+    if (populate) return slmgs_populate(c);
+    return SLMGS_OK;
+}
+
+static int run_impl(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
     if (n_iter < 0) return fail(c, SLMGS_ERR_INVALID, "n_iter < 0");
     if (n_iter > 0 && !params) return fail(c, SLMGS_ERR_INVALID, "params is NULL");
     for (int i = 0; i < n_iter; ++i) {
@@ -734,6 +870,7 @@ extern "C" int slmgs_run(slmgs_ctx* c, const slmgs_params* params, int n_iter, i
             return fail(c, SLMGS_ERR_STATE, "spot feedback without slmgs_set_spots");
     }
     int e;
+    if ((e = prepare_sparse(c, params, n_iter))) return e;
     if (n_iter > 0) {
         // a weight update is done inside the fused kernel when it has no global dependency within the
         // iteration (the L2 renormalisation is deferred by one kernel, see DESIGN.md "Lazy normalisation")
@@ -780,8 +917,6 @@ extern "C" int slmgs_run(slmgs_ctx* c, const slmgs_params* params, int n_iter, i
             if ((e = run_row(c, ROW_FUSED, ra))) return e;
         }
     }
-    c->ff_valid = false;
-    if (populate) return slmgs_populate(c);
     return SLMGS_OK;
 }
 
@@ -888,6 +1023,8 @@ extern "C" int slmgs_set_spots(slmgs_ctx* c, int n, const int* x, const int* y, 
     RT(c, rt_h2d(c->spot_y, y, (size_t)n * sizeof(int), c->stream));
     RT(c, rt_h2d(c->spot_amp, spot_amp, (size_t)n * sizeof(float), c->stream));
     c->n_spots = n;
+    c->spot_x_h.assign(x, x + n);
+    c->tile_key = -1;
     return SLMGS_OK;
 }
 

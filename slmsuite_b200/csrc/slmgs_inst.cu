@@ -14,10 +14,22 @@ namespace slmgs {
 int SLMGS_CAT(launch_row_, SLMGS_N)(int mode, int gx, int gy, int nthreads, rt_stream s, const RowArgs& a) {
     switch (mode) {
         case ROW_FIRST: {
+            if (a.colflag) {
+                typedef RowKernel<SLMGS_N, ROW_FIRST, false, true> K;
+                return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
+            }
             typedef RowKernel<SLMGS_N, ROW_FIRST> K;
             return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
         }
         case ROW_FUSED: {
+            if (a.colflag) {  // sparse far field: only the column tiles the column kernel processes are moved
+                if (a.store_phase) {
+                    typedef RowKernel<SLMGS_N, ROW_FUSED, true, true> K;
+                    return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
+                }
+                typedef RowKernel<SLMGS_N, ROW_FUSED, false, true> K;
+                return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
+            }
             if (a.store_phase) {
                 typedef RowKernel<SLMGS_N, ROW_FUSED, true> K;
                 return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);

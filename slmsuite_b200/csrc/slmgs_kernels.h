@@ -171,10 +171,15 @@ struct RowArgs {
     int zero_bs;
     int pdl;             // launch with programmatic dependent launch
     int pf_dist;         // L2 prefetch distance in tiles (blocks resident on the GPU), 0 = off
+    const unsigned char* colflag;  // sparse far field: one byte per column tile of the column kernel (1 = the tile is
+                                   // processed by the column kernel); columns of other tiles are identically zero after
+                                   // the far-field constraint, so they are neither stored nor loaded.  nullptr = dense
+    int ctile_shift;               // log2(columns per column tile)
 };
 
 // STORE (ROW_FUSED only): this launch also writes the phase (last iteration of a fused run)
-template <int N, int MODE, bool STORE = false> struct RowKernel {
+// SPARSE (ROW_FIRST / ROW_FUSED): spectrum columns are filtered through a.colflag
+template <int N, int MODE, bool STORE = false, bool SPARSE = false> struct RowKernel {
     typedef Fft<N> F;
     typedef RowArgs Args;
     static constexpr int E = F::E, NS = F::NS;
@@ -234,7 +239,9 @@ template <int N, int MODE, bool STORE = false> struct RowKernel {
             SLMGS_UNROLL
             for (int m = 0; m < R; ++m) {
                 const int k = F::last_index(L.lt + F::TPL * u, m);
-                st.v[u * R + m] = L.active ? ld_stream(a.fld + L.fbase + k) : cmake(0.f, 0.f);
+                bool on = L.active;
+                if (SPARSE) on = on && __ldg(a.colflag + (k >> a.ctile_shift)) != 0;
+                st.v[u * R + m] = on ? ld_stream(a.fld + L.fbase + k) : cmake(0.f, 0.f);
             }
         }
     }
@@ -244,7 +251,11 @@ template <int N, int MODE, bool STORE = false> struct RowKernel {
         SLMGS_UNROLL
         for (int u = 0; u < E / R; ++u) {
             SLMGS_UNROLL
-            for (int m = 0; m < R; ++m) a.fld[L.fbase + F::last_index(L.lt + F::TPL * u, m)] = st.v[u * R + m];
+            for (int m = 0; m < R; ++m) {
+                const int k = F::last_index(L.lt + F::TPL * u, m);
+                if (SPARSE && __ldg(a.colflag + (k >> a.ctile_shift)) == 0) continue;
+                a.fld[L.fbase + k] = st.v[u * R + m];
+            }
         }
     }
     // v <- amp * exp(i (phase + prop)) zero-padded: _hologram.py:1000-1011
@@ -399,6 +410,8 @@ struct ColArgs {
     int store_ampff, store_phaseff, store_farfield;  // COL_FWD outputs
     int pdl;              // launch with programmatic dependent launch
     int pf_dist;          // L2 prefetch distance in tiles (blocks resident on the GPU), 0 = off
+    const int* tiles;     // sparse far field: blockIdx.x -> column tile (only tiles whose constrained far field can be
+                          // non-zero are launched), or nullptr = every tile, in order
 };
 
 // CT: columns per tile known at compile time (block of MAXT threads), 0 = derived from blockDim at run time
@@ -430,12 +443,13 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
         L.C = CT > 0 ? CT : id.nthreads / F::TPL;  // a power of two
         L.col = id.tid & (L.C - 1);
         L.lt = id.tid >> ilog2(L.C);
-        L.gc = id.bx * L.C + L.col;
+        const int tile = a.tiles ? __ldg(a.tiles + id.bx) : id.bx;
+        L.gc = tile * L.C + L.col;
         L.s = smem + L.col;
         L.fbase = (long long)id.by * a.fld_bs + L.gc;
         // far-field-shaped images are tile-major: [W/C tiles][H rows][C columns] (image_index below)
-        L.ibase = (long long)id.by * a.img_bs + (long long)id.bx * a.H * L.C + L.col;
-        L.tbase = (long long)id.by * a.target_bs + (long long)id.bx * a.H * L.C + L.col;
+        L.ibase = (long long)id.by * a.img_bs + (long long)tile * a.H * L.C + L.col;
+        L.tbase = (long long)id.by * a.target_bs + (long long)tile * a.H * L.C + L.col;
         return L;
     }
     // Rows of `fld` that hold the SLM (rolled index n): ((n + H/2) mod H) - i0 in [0, h).  Row n of butterfly
@@ -604,7 +618,7 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
         } else {
             if constexpr (P == 0) {
                 load_rows(st, a, L);
-                if (a.pf_dist > 0 && a.h == a.H) {
+                if (a.pf_dist > 0 && a.h == a.H && !a.tiles) {
                     // dense field: pull the rows of the tile group this SM will run next into L2 (a 128-byte line
                     // holds 16 columns = several tiles, so one tile of each line-sharing group issues the prefetch)
                     const int per_line = 16 / L.C > 0 ? 16 / L.C : 1;

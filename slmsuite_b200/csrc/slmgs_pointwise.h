@@ -306,4 +306,47 @@ struct SpotUpdateKernel {
     }
 };
 
+// ------------------------------------------------------------------------------------------
+// Column-tile occupancy for the sparse fused loop.  The constrained far field farfield = weights *
+// exp(i phase_ff) (_hologram.py:1601-1605) is identically zero wherever weights == 0 -- and a weight that
+// is zero stays zero under every WGS update (:1870, W *= fc with fc finite) -- except in an MRAF noise
+// region (target is NaN, :1643-1653), which passes the field through.  One block per (tile, hologram):
+//   flags[tile] |= 1 if any weight of the tile is non-zero (or NaN), |= 2 if any target value is NaN.
+// The images are tile-major, so a tile is one contiguous block of H*C floats.
+// ------------------------------------------------------------------------------------------
+struct TileArgs {
+    const float* weights;
+    const float* target;
+    long long img_bs, target_bs;
+    long long tile_elems;  // H * C
+    int* flags;            // [W / C], zeroed by the caller
+};
+
+#ifndef SLMGS_EMULATE
+SLMGS_DEVICE void atomic_or_int(int* p, int v) { atomicOr(p, v); }
+#else
+inline void atomic_or_int(int* p, int v) { *p |= v; }
+#endif
+
+struct TileFlagKernel {
+#ifndef SLMGS_EMULATE
+    static SLMGS_DEVICE void barrier(const ThreadId&) { __syncthreads(); }
+#endif
+    typedef TileArgs Args;
+    static constexpr int MAXT = 256;
+    static constexpr int NPHASE = 1;
+    struct State {};
+    template <int P> static SLMGS_DEVICE void phase(State&, const Args& a, cf*, const ThreadId& id) {
+        const float* w = a.weights + (long long)id.by * a.img_bs + (long long)id.bx * a.tile_elems;
+        const float* t = a.target + (long long)id.by * a.target_bs + (long long)id.bx * a.tile_elems;
+        int f = 0;
+        for (long long i = id.tid; i < a.tile_elems; i += id.nthreads) {
+            const float wv = ld_stream(w + i), tv = ld_stream(t + i);
+            if (!(wv == 0.0f)) f |= 1;
+            if (tv != tv) f |= 2;
+        }
+        if (f) atomic_or_int(a.flags + id.bx, f);
+    }
+};
+
 }  // namespace slmgs

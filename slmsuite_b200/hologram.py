@@ -416,6 +416,21 @@ class Hologram:
             self._ctx, bitdepth, None if corr is None else _lib.dptr(corr), out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def set_sparse(self, enabled=True):
+        """
+        Not in the reference.  Switches the sparse far-field path of the fused loop (default: automatic).  When the
+        weights are zero on whole column tiles -- spot targets -- those tiles cannot contribute to
+        ``farfield = weights * exp(i phase_ff)`` (_hologram.py:1601-1605), so the column kernels skip them and the
+        row kernels do not move their columns.  Results are identical to the dense loop.
+        """
+        self._check(self._lib.slmgs_set_sparse(self._ctx, 1 if enabled else 0))
+
+    def sparse_info(self):
+        """(last fused run used the sparse path, active column tiles, column tiles)."""
+        out = np.zeros(3, dtype=np.int32)
+        self._check(self._lib.slmgs_sparse_info(self._ctx, _lib.iptr(out)))
+        return bool(out[0]), int(out[1]), int(out[2])
+
     def get_amp(self):
         """_hologram.py:813-826."""
         return self._amp

@@ -32,16 +32,24 @@ def spots(shape, n, seed):
     return t
 
 
+def tag(h):
+    used, n, m = h.sparse_info()
+    return f"  [sparse far field: {n}/{m} column tiles]" if used else "  [dense]"
+
+
+if "--dense" in sys.argv:  # force the dense loop (every column tile processed)
+    sys.argv.remove("--dense")
+    os.environ["SLMGS_SPARSE"] = "0"
 which = sys.argv[1:] or ["1", "2", "2d", "3", "4", "5", "mp", "gray", "refbench"]
 rng = np.random.default_rng(0)
 if "1" in which:
     h = Hologram(rng.random((512, 512), dtype=np.float32), phase=rng.uniform(-3, 3, (512, 512)).astype(np.float32))
     ms = timed(h, 5, method="GS", maxiter=30)
-    print(f"config1 GS 512^2 30 it: {ms:.3f} ms/optimize -> {30/ms*1e3:.0f} it/s")
+    print(f"config1 GS 512^2 30 it: {ms:.3f} ms/optimize -> {30/ms*1e3:.0f} it/s" + tag(h))
 if "2" in which:
     h = Hologram(spots((4096, 4096), 64, 1), phase=rng.uniform(-3, 3, (1152, 1920)).astype(np.float32), slm_shape=(1152, 1920))
     ms = timed(h, 3, method="WGS-Kim", maxiter=50)
-    print(f"config2 WGS-Kim 4096^2 (slm 1152x1920) 50 it: {ms:.3f} ms/optimize -> {50/ms*1e3:.0f} it/s")
+    print(f"config2 WGS-Kim 4096^2 (slm 1152x1920) 50 it: {ms:.3f} ms/optimize -> {50/ms*1e3:.0f} it/s" + tag(h))
 if "2d" in which:
     h = Hologram(rng.random((4096, 4096), dtype=np.float32), phase=rng.uniform(-3, 3, (4096, 4096)).astype(np.float32))
     ms = timed(h, 3, method="GS", maxiter=50)
@@ -52,14 +60,14 @@ if "3" in which:
     h = SpotHologram.make_rectangular_array((4096, 4096), array_shape=(32, 32), array_pitch=(64, 64), basis="knm")
     h.reset_phase(rng.uniform(-3, 3, (4096, 4096)).astype(np.float32))
     ms = timed(h, 2, method="WGS-Leonardo", maxiter=100, feedback="computational_spot")
-    print(f"config3 SpotHologram 32x32 on 4096^2 WGS-Leonardo spot feedback 100 it: {ms:.3f} ms/optimize -> {100/ms*1e3:.0f} it/s")
+    print(f"config3 SpotHologram 32x32 on 4096^2 WGS-Leonardo spot feedback 100 it: {ms:.3f} ms/optimize -> {100/ms*1e3:.0f} it/s" + tag(h))
 if "4" in which:
     B = 8
     T = np.stack([spots((2048, 2048), 100, 100 + b) for b in range(B)])
     P = rng.uniform(-3, 3, (B, 2048, 2048)).astype(np.float32)
     h = HologramBatch(T, phase=P)
     ms = timed(h, 3, method="GS", maxiter=50)
-    print(f"config4 shard: batch of {B} 2048^2 GS 50 it: {ms:.3f} ms/optimize -> {B*50/ms*1e3:.0f} hologram-it/s per GPU")
+    print(f"config4 shard: batch of {B} 2048^2 GS 50 it: {ms:.3f} ms/optimize -> {B*50/ms*1e3:.0f} hologram-it/s per GPU" + tag(h))
 if "5" in which:
     v = np.random.default_rng(5).uniform(64, 8192 - 64, (2, 10000))
     t0 = time.time()
@@ -67,7 +75,7 @@ if "5" in which:
     h.reset_phase(rng.uniform(-3, 3, (8192, 8192)).astype(np.float32))
     print(f"config5 ctor {time.time()-t0:.1f} s")
     ms = timed(h, 1, method="WGS-Leonardo", maxiter=20, feedback="computational_spot")
-    print(f"config5 SpotHologram 10k spots 8192^2 WGS-Leonardo spot feedback 20 it: {ms:.3f} ms/optimize -> {20/ms*1e3:.0f} it/s")
+    print(f"config5 SpotHologram 10k spots 8192^2 WGS-Leonardo spot feedback 20 it: {ms:.3f} ms/optimize -> {20/ms*1e3:.0f} it/s" + tag(h))
 if "mp" in which:
     slm = (1152, 1920)
     ph = rng.uniform(-3, 3, slm).astype(np.float32)
@@ -100,4 +108,4 @@ if "refbench" in which:
     for method in ("GS", "WGS-Leonardo", "WGS-Kim", "WGS-Nogrette"):
         h = Hologram(spots((1024, 1024), 20, 7), phase=rng.uniform(-3, 3, (1024, 1024)).astype(np.float32))
         ms = timed(h, 5, method=method, maxiter=20)
-        print(f"reference benchmark test_gs_speed[{method}] 1024^2 20 it: {ms:.3f} ms/optimize -> {20/ms*1e3:.0f} it/s")
+        print(f"reference benchmark test_gs_speed[{method}] 1024^2 20 it: {ms:.3f} ms/optimize -> {20/ms*1e3:.0f} it/s" + tag(h))

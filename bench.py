@@ -365,6 +365,13 @@ def run_b200(args, rank, local_rank, world):
     sp_e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - e0))
     barrier()
     sp_info = ws.holo.sparse_info()
+    ws.holo._check(lib.slmgs_profile_enable(ws.ctx, 1))
+    for _ in range(args.steps):
+        ws.step_resident()
+    sp_prof_ms = (C.c_float * 6)()
+    sp_prof_n = (C.c_int * 6)()
+    ws.holo._check(lib.slmgs_profile_read(ws.ctx, sp_prof_ms, sp_prof_n))
+    ws.holo._check(lib.slmgs_profile_enable(ws.ctx, 0))
 
     iters_total = world * args.steps * ITERS
     value = iters_total / (total_ms * 1e-3)
@@ -374,6 +381,9 @@ def run_b200(args, rank, local_rank, world):
         "value": iters_total / (sp_total_ms * 1e-3), "unit": "it/s", "ms_per_step": sp_total_ms / args.steps,
         "e2e": {"value": iters_total / (sp_e2e_ms * 1e-3), "unit": "it/s", "ms_per_step": sp_e2e_ms / args.steps},
         "gpu_launches": int(sp_launches),
+        "kernels": {n: {"launches": int(sp_prof_n[k]), "avg_ms": float(sp_prof_ms[k]) / int(sp_prof_n[k])}
+                    for k, n in enumerate(["row_first", "row_fused", "row_last", "col_forward", "col_fused", "col_inverse"])
+                    if sp_prof_n[k]},
         "sparse_path_used": bool(sp_info[0]), "active_column_tiles": int(sp_info[1]), "column_tiles": int(sp_info[2]),
         "note": "same config and code path; column tiles whose weights are all zero are skipped (identical results, "
                 "tests/test_sparse.py); not the headline because it depends on the target",

@@ -109,6 +109,15 @@ SLMGS_API int slmgs_get_farfield(slmgs_ctx*, float* farfield_c64);        /* int
  * uint16; correction = optional float64 [h][w] wavefront correction (source["phase"]) or NULL. */
 SLMGS_API int slmgs_get_phase_gray(slmgs_ctx*, int bitdepth, const double* correction, void* out);
 
+/* "next" row: what a simulated camera sees, SimulatedCamera._get_image_hw,
+ * hardware/cameras/simulated.py:344-402: out[b][i] = clip(|farfield|^2 sampled at (ky[i], kx[i]) with
+ * scipy.ndimage.map_coordinates(order=0) semantics (nearest pixel, 0 outside [0, len-1]) * scale, clip_max), cast to
+ * out_kind (0 float32, 1 uint8, 2 uint16; clip_max < 0 = no clipping).  Coordinates are float64 pixel coordinates of
+ * the centred far field (the reference's knm_cam, simulated.py:180-185); the grid stays on the device between calls.
+ * The far field is recomputed from the current phase (this refreshes amp_ff like get_farfield, _hologram.py:922-929). */
+SLMGS_API int slmgs_set_sample_grid(slmgs_ctx*, long long n, const double* ky, const double* kx);
+SLMGS_API int slmgs_sample_intensity(slmgs_ctx*, float scale, float clip_max, int out_kind, void* out);
+
 /* ---- fused loop -------------------------------------------------------------------------- */
 /* optimize_gs with callback=None and no per-iteration statistics (:1465-1493):
  * n_iter iterations, then _populate_results (:934-949).  params[i] are the flags of iteration i

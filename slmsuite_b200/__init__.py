@@ -10,6 +10,7 @@ from .hologram import ALGORITHM_DEFAULTS, ALGORITHM_INDEX, FEEDBACK_OPTIONS, Hol
 from .spots import SpotHologram
 from .batch import HologramBatch, optimize_sharded, shard_bounds
 from .multiplane import MultiplaneHologram
+from .camera import SimulatedCamera
 
-__all__ = ["Hologram", "SpotHologram", "HologramBatch", "MultiplaneHologram", "optimize_sharded", "shard_bounds", "ALGORITHM_DEFAULTS", "ALGORITHM_INDEX", "FEEDBACK_OPTIONS"]
+__all__ = ["Hologram", "SpotHologram", "HologramBatch", "MultiplaneHologram", "SimulatedCamera", "optimize_sharded", "shard_bounds", "ALGORITHM_DEFAULTS", "ALGORITHM_INDEX", "FEEDBACK_OPTIONS"]
 __version__ = "0.1.0"

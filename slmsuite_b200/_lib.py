@@ -77,6 +77,8 @@ SIGNATURES = {
     "slmgs_get_amp_ff": (C.c_int, [_ctx, _fp]),
     "slmgs_get_farfield": (C.c_int, [_ctx, _fp]),
     "slmgs_get_phase_gray": (C.c_int, [_ctx, C.c_int, _dp, C.c_void_p]),
+    "slmgs_set_sample_grid": (C.c_int, [_ctx, C.c_longlong, _dp, _dp]),
+    "slmgs_sample_intensity": (C.c_int, [_ctx, C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "slmgs_run": (C.c_int, [_ctx, _pp, C.c_int, C.c_int]),
     "slmgs_set_sparse": (C.c_int, [_ctx, C.c_int]),
     "slmgs_sparse_info": (C.c_int, [_ctx, _ip]),

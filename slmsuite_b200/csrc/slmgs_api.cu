@@ -146,6 +146,10 @@ struct slmgs_ctx {
     int tile_key;                  // (mraf, spot width) the device list was built for, -1 = none
     int n_active;                  // tiles in tile_list
     bool sparse_now;               // the launches being issued use the tile list
+    // camera sampling grid (slmgs_set_sample_grid)
+    double* samp_y;
+    double* samp_x;
+    long long n_samp;
     bool last_sparse;              // the last slmgs_run used it
     // timing
     bool profiling;
@@ -302,6 +306,8 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
     c->tile_key = -1;
     c->n_active = 0;
     c->sparse_now = false;
+    c->samp_y = c->samp_x = nullptr;
+    c->n_samp = 0;
     c->last_sparse = false;
     c->sref = nullptr;
     c->profiling = false;
@@ -367,7 +373,7 @@ extern "C" int slmgs_destroy(slmgs_ctx* c) {
     void* ptrs[] = {c->fld, c->farfield, c->stage_c, c->stage_f, c->phase, c->amp, c->prop, c->target,
                     c->weights, c->phase_ff, c->amp_ff, c->twA_row, c->twB_row, c->twA_col, c->twB_col, c->acc,
                     c->partial, c->spot_x, c->spot_y, c->spot_amp, c->spot_pw, c->phase_saved, c->mp_sum, c->zero_w,
-                    c->tile_flags, c->tile_list, c->tile_byte};
+                    c->tile_flags, c->tile_list, c->tile_byte, c->samp_y, c->samp_x};
     for (void* p : ptrs)
         if (p) rt_free(p);
 #ifndef SLMGS_EMULATE
@@ -970,6 +976,52 @@ extern "C" int slmgs_get_farfield(slmgs_ctx* c, float* out) {
     if ((e = launch_elem<EW_ROLL_C64>(c, a, c->B))) return e;
     RT(c, rt_d2h(out, c->stage_c, (size_t)c->B * P * sizeof(cf), c->stream));
     return SLMGS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// camera sampling of |farfield|^2 (SimulatedCamera._get_image_hw, hardware/cameras/simulated.py:344-402)
+// ------------------------------------------------------------------------------------------
+extern "C" int slmgs_set_sample_grid(slmgs_ctx* c, long long n, const double* ky, const double* kx) {
+    CHECK_CTX(c);
+    if (n < 1 || !ky || !kx) return fail(c, SLMGS_ERR_INVALID, "bad sampling grid");
+    RT(c, rt_sync(c->stream));
+    if (c->samp_y) { rt_free(c->samp_y); rt_free(c->samp_x); c->samp_y = c->samp_x = nullptr; c->n_samp = 0; }
+    int e;
+    if ((e = dev_alloc(c, &c->samp_y, (size_t)n))) return e;
+    if ((e = dev_alloc(c, &c->samp_x, (size_t)n))) return e;
+    RT(c, rt_h2d(c->samp_y, ky, (size_t)n * sizeof(double), c->stream));
+    RT(c, rt_h2d(c->samp_x, kx, (size_t)n * sizeof(double), c->stream));
+    c->n_samp = n;
+    return SLMGS_OK;
+}
+
+extern "C" int slmgs_sample_intensity(slmgs_ctx* c, float scale, float clip_max, int out_kind, void* out) {
+    CHECK_CTX(c);
+    if (!out) return fail(c, SLMGS_ERR_INVALID, "out is NULL");
+    if (out_kind < 0 || out_kind > 2) return fail(c, SLMGS_ERR_INVALID, "out_kind must be 0 (float32), 1 (uint8) or 2 (uint16)");
+    if (c->n_samp < 1) return fail(c, SLMGS_ERR_STATE, "sample_intensity without slmgs_set_sample_grid");
+    int e;
+    // far field of the current phase (like get_farfield, this refreshes amp_ff; _hologram.py:922-929)
+    if ((e = forward_impl(c, c->farfield ? 1 : 0, 1, 0, true))) return e;
+    c->ff_valid = c->farfield != nullptr;
+    const size_t esz = out_kind == 0 ? 4 : out_kind == 1 ? 1 : 2;
+    const size_t bytes = (size_t)c->B * (size_t)c->n_samp * esz;
+    void* dout = nullptr;
+    if ((e = rt_check(c, rt_malloc(&dout, bytes), "device allocation"))) return e;
+    SampleArgs a;
+    memset(&a, 0, sizeof a);
+    a.amp_ff = c->amp_ff; a.img_bs = (long long)c->H * c->W;
+    a.ky = c->samp_y; a.kx = c->samp_x; a.n = c->n_samp;
+    a.out = dout; a.out_kind = out_kind; a.scale = scale; a.clip_max = clip_max;
+    a.H = c->H; a.W = c->W; a.C = c->col_threads / c->icol.tpl;
+    long long blocks = (c->n_samp + 255) / 256;
+    if (blocks > (long long)c->sms * 16) blocks = (long long)c->sms * 16;
+    c->launches++;
+    e = rt_check(c, launch_kernel<SampleKernel>((int)blocks, c->B, 256, 0, c->stream, a), "sample launch");
+    if (!e) e = rt_check(c, rt_d2h(out, dout, bytes, c->stream), "d2h");
+    rt_sync(c->stream);
+    rt_free(dout);
+    return e;
 }
 
 // pixel feedback on amp_ff (must hold |farfield| of the current iteration): _hologram.py:1822-1879

@@ -349,4 +349,55 @@ struct TileFlagKernel {
     }
 };
 
+// ------------------------------------------------------------------------------------------
+// Camera sampling of the far-field intensity ("next" row):
+// SimulatedCamera._get_image_hw, hardware/cameras/simulated.py:344-402:
+//     img = map_coordinates(|farfield|^2, knm_cam, order=0);  img *= exposure * gain;
+//     img[img > bitresolution - 1] = bitresolution - 1;  img.astype(dtype)
+// scipy.ndimage.map_coordinates(order=0, mode="constant", cval=0): a coordinate outside [0, len-1] gives 0,
+// otherwise the sample at floor(c + 0.5).  Coordinates are float64 (y, x) in the reference's centred far-field
+// convention; amp_ff is rolled and tile-major on the device.
+// ------------------------------------------------------------------------------------------
+struct SampleArgs {
+    const float* amp_ff;  // [B][H][W] rolled, tile-major
+    long long img_bs;
+    const double* ky;     // [n]
+    const double* kx;     // [n]
+    long long n;
+    void* out;            // [B][n] float32 / uint8 / uint16
+    int out_kind;         // 0 float32, 1 uint8, 2 uint16
+    float scale;          // exposure * gain (applied in float32 like the reference's in-place multiply)
+    float clip_max;       // bitresolution - 1, or < 0 for no clipping
+    int H, W, C;
+};
+
+struct SampleKernel {
+#ifndef SLMGS_EMULATE
+    static SLMGS_DEVICE void barrier(const ThreadId&) { __syncthreads(); }
+#endif
+    typedef SampleArgs Args;
+    static constexpr int MAXT = 256;
+    static constexpr int NPHASE = 1;
+    struct State {};
+    template <int P> static SLMGS_DEVICE void phase(State&, const Args& a, cf*, const ThreadId& id) {
+        const float* img = a.amp_ff + (long long)id.by * a.img_bs;
+        const long long stride = (long long)id.gx * id.nthreads;
+        for (long long i = (long long)id.bx * id.nthreads + id.tid; i < a.n; i += stride) {
+            const double cy = a.ky[i], cx = a.kx[i];
+            float v = 0.0f;
+            if (cy >= 0.0 && cy <= (double)(a.H - 1) && cx >= 0.0 && cx <= (double)(a.W - 1)) {
+                const int y = (int)floor(cy + 0.5), x = (int)floor(cx + 0.5);
+                const float f = img[image_index((y + (a.H >> 1)) % a.H, (x + (a.W >> 1)) % a.W, a.H, a.C)];
+                v = f * f;
+            }
+            v = v * a.scale;
+            if (a.clip_max >= 0.0f && v > a.clip_max) v = a.clip_max;
+            const long long o = (long long)id.by * a.n + i;
+            if (a.out_kind == 0) reinterpret_cast<float*>(a.out)[o] = v;
+            else if (a.out_kind == 1) reinterpret_cast<unsigned char*>(a.out)[o] = (unsigned char)v;
+            else reinterpret_cast<unsigned short*>(a.out)[o] = (unsigned short)v;
+        }
+    }
+};
+
 }  // namespace slmgs

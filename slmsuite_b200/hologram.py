@@ -235,6 +235,20 @@ class Hologram:
         """Near-field source amplitude: scalar (np.float64) or L2-normalised array (_hologram.py:401-405)."""
         return self._amp
 
+    @amp.setter
+    def amp(self, value):
+        """The reference stores ``amp`` as a plain attribute that users (and ``SimulatedCamera._get_image_hw``,
+        hardware/cameras/simulated.py:364) overwrite WITHOUT normalisation; the same here."""
+        if np.ndim(value) == 0:
+            self._amp = value
+            self._check(self._lib.slmgs_set_amp_scalar(self._ctx, float(value)))
+        else:
+            a = np.array(value, dtype=self.dtype)
+            if a.shape != tuple(self.slm_shape):
+                raise ValueError(f"amp of shape {a.shape} is not of slm_shape {self.slm_shape}")
+            self._amp = a
+            self._check(self._lib.slmgs_set_amp_array(self._ctx, _lib.fptr(_lib.f32(a)), 0))
+
     @property
     def phase(self):
         """Near-field phase, shape ``slm_shape`` (downloaded)."""

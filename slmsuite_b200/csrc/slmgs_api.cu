@@ -128,6 +128,7 @@ struct slmgs_ctx {
     // host-side state
     float amp_scalar;
     int amp_per_hologram;
+    size_t amp_count;  // elements allocated for amp
     int target_shared;
     int w_pending;     // accumulator slot of a not-yet-applied weight normalisation, or -1
     bool ff_valid;     // farfield / amp_ff hold the transform of the current phase (stepped mode)
@@ -146,6 +147,10 @@ struct slmgs_ctx {
     int tile_key;                  // (mraf, spot width) the device list was built for, -1 = none
     int n_active;                  // tiles in tile_list
     bool sparse_now;               // the launches being issued use the tile list
+    // grow-only device scratch for small downloads (gray levels, camera images): cudaMalloc / cudaFree per call
+    // cost milliseconds once the process holds gigabytes of allocations
+    void* scratch;
+    size_t scratch_bytes;
     // camera sampling grid (slmgs_set_sample_grid)
     double* samp_y;
     double* samp_x;
@@ -188,6 +193,22 @@ template <class T> static int dev_alloc(slmgs_ctx* c, T** p, size_t count) {
     int e = rt_malloc(&q, count * sizeof(T));
     if (e) return rt_check(c, e, "device allocation");
     *p = (T*)q;
+    return 0;
+}
+
+static int scratch_reserve(slmgs_ctx* c, size_t bytes, void** out) {
+    if (bytes > c->scratch_bytes) {
+        if (c->scratch) {
+            RT(c, rt_sync(c->stream));
+            rt_free(c->scratch);
+            c->scratch = nullptr;
+            c->scratch_bytes = 0;
+        }
+        int e = rt_check(c, rt_malloc(&c->scratch, bytes), "device allocation");
+        if (e) return e;
+        c->scratch_bytes = bytes;
+    }
+    *out = c->scratch;
     return 0;
 }
 
@@ -292,6 +313,7 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
     c->spot_x = c->spot_y = nullptr; c->spot_amp = nullptr; c->spot_pw = nullptr; c->n_spots = 0;
     c->amp_scalar = (float)(1.0 / sqrt((double)h * (double)w));
     c->amp_per_hologram = 0;
+    c->amp_count = 0;
     c->target_shared = 0;
     c->w_pending = -1;
     c->ff_valid = false;
@@ -308,6 +330,8 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
     c->sparse_now = false;
     c->samp_y = c->samp_x = nullptr;
     c->n_samp = 0;
+    c->scratch = nullptr;
+    c->scratch_bytes = 0;
     c->last_sparse = false;
     c->sref = nullptr;
     c->profiling = false;
@@ -373,7 +397,7 @@ extern "C" int slmgs_destroy(slmgs_ctx* c) {
     void* ptrs[] = {c->fld, c->farfield, c->stage_c, c->stage_f, c->phase, c->amp, c->prop, c->target,
                     c->weights, c->phase_ff, c->amp_ff, c->twA_row, c->twB_row, c->twA_col, c->twB_col, c->acc,
                     c->partial, c->spot_x, c->spot_y, c->spot_amp, c->spot_pw, c->phase_saved, c->mp_sum, c->zero_w,
-                    c->tile_flags, c->tile_list, c->tile_byte, c->samp_y, c->samp_x};
+                    c->tile_flags, c->tile_list, c->tile_byte, c->samp_y, c->samp_x, c->scratch};
     for (void* p : ptrs)
         if (p) rt_free(p);
 #ifndef SLMGS_EMULATE
@@ -501,14 +525,17 @@ extern "C" int slmgs_set_amp_array(slmgs_ctx* c, const float* amp, int per_holog
     CHECK_CTX(c);
     if (!amp) return fail(c, SLMGS_ERR_INVALID, "amp is NULL");
     const size_t S = (size_t)c->h * c->w, n = per_hologram ? S * c->B : S;
-    if (c->amp) {
+    if (c->amp && c->amp_count != n) {
         RT(c, rt_sync(c->stream));
         rt_free(c->amp);
         c->amp = nullptr;
     }
-    int e = dev_alloc(c, &c->amp, n);
-    if (e) return e;
-    RT(c, rt_h2d(c->amp, amp, n * sizeof(float), c->stream));
+    if (!c->amp) {
+        int e = dev_alloc(c, &c->amp, n);
+        if (e) return e;
+        c->amp_count = n;
+    }
+    RT(c, rt_h2d(c->amp, amp, n * sizeof(float), c->stream));  // stream-ordered after the kernels that read the old one
     c->amp_per_hologram = per_hologram ? 1 : 0;
     // Parseval: ||farfield|| = ||nearfield|| = ||amp|| (first hologram's amp is representative: the
     // constructor L2-normalises every amp, _hologram.py:404-405)
@@ -592,28 +619,22 @@ extern "C" int slmgs_get_phase_gray(slmgs_ctx* c, int bitdepth, const double* co
     if (bitdepth < 1 || bitdepth > 16) return fail(c, SLMGS_ERR_INVALID, "bitdepth must be in [1, 16]");
     const long long S = (long long)c->h * c->w;
     const int out16 = bitdepth > 8;
-    const size_t out_bytes = (size_t)c->B * S * (out16 ? 2 : 1);
+    const size_t out_bytes = ((size_t)c->B * S * (out16 ? 2 : 1) + 7) & ~(size_t)7;
     int e;
-    double* dcorr = nullptr;
-    void* dout = nullptr;
-    e = rt_check(c, rt_malloc(&dout, out_bytes), "device allocation");
-    if (!e && correction) {
-        e = dev_alloc(c, &dcorr, (size_t)S);
-        if (!e) e = rt_check(c, rt_h2d(dcorr, correction, (size_t)S * sizeof(double), c->stream), "h2d");
-    }
-    if (!e) {
-        ElemArgs a = elem_args(c, c->phase, dout, S);
-        a.corr = dcorr;
-        a.bitres = 1 << bitdepth;
-        a.factor = -((double)a.bitres / 2.0 / 3.14159265358979323846);
-        a.out16 = out16;
-        e = launch_elem<EW_PHASE2GRAY>(c, a, c->B);
-    }
-    if (!e) e = rt_check(c, rt_d2h(out, dout, out_bytes, c->stream), "d2h");
-    rt_sync(c->stream);
-    if (dout) rt_free(dout);
-    if (dcorr) rt_free(dcorr);
-    return e;
+    void* buf = nullptr;
+    if ((e = scratch_reserve(c, out_bytes + (correction ? (size_t)S * sizeof(double) : 0), &buf))) return e;
+    void* dout = buf;
+    double* dcorr = correction ? reinterpret_cast<double*>(reinterpret_cast<char*>(buf) + out_bytes) : nullptr;
+    if (correction) RT(c, rt_h2d(dcorr, correction, (size_t)S * sizeof(double), c->stream));
+    ElemArgs a = elem_args(c, c->phase, dout, S);
+    a.corr = dcorr;
+    a.bitres = 1 << bitdepth;
+    a.factor = -((double)a.bitres / 2.0 / 3.14159265358979323846);
+    a.out16 = out16;
+    if ((e = launch_elem<EW_PHASE2GRAY>(c, a, c->B))) return e;
+    RT(c, rt_d2h(out, dout, (size_t)c->B * S * (out16 ? 2 : 1), c->stream));
+    RT(c, rt_sync(c->stream));
+    return SLMGS_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1007,7 +1028,7 @@ extern "C" int slmgs_sample_intensity(slmgs_ctx* c, float scale, float clip_max,
     const size_t esz = out_kind == 0 ? 4 : out_kind == 1 ? 1 : 2;
     const size_t bytes = (size_t)c->B * (size_t)c->n_samp * esz;
     void* dout = nullptr;
-    if ((e = rt_check(c, rt_malloc(&dout, bytes), "device allocation"))) return e;
+    if ((e = scratch_reserve(c, bytes, &dout))) return e;
     SampleArgs a;
     memset(&a, 0, sizeof a);
     a.amp_ff = c->amp_ff; a.img_bs = (long long)c->H * c->W;
@@ -1020,7 +1041,6 @@ extern "C" int slmgs_sample_intensity(slmgs_ctx* c, float scale, float clip_max,
     e = rt_check(c, launch_kernel<SampleKernel>((int)blocks, c->B, 256, 0, c->stream, a), "sample launch");
     if (!e) e = rt_check(c, rt_d2h(out, dout, bytes, c->stream), "d2h");
     rt_sync(c->stream);
-    rt_free(dout);
     return e;
 }
 

@@ -50,10 +50,19 @@ SLMGS_DEVICE float2 ld_stream(const float2* p) {
     return v;
 }
 SLMGS_DEVICE void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+SLMGS_DEVICE void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// cached (L1-allocating) load for data that was prefetched into L1
+SLMGS_DEVICE float ld_cached(const float* p) {
+    float v;
+    asm volatile("ld.global.ca.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
 #else
 inline float ld_stream(const float* p) { return *p; }
 inline float2 ld_stream(const float2* p) { return *p; }
 inline void prefetch_l2(const void*) {}
+inline void prefetch_l1(const void*) {}
+inline float ld_cached(const float* p) { return *p; }
 #endif
 
 // log2 of a power of two

@@ -40,7 +40,7 @@ def tag(h):
 if "--dense" in sys.argv:  # force the dense loop (every column tile processed)
     sys.argv.remove("--dense")
     os.environ["SLMGS_SPARSE"] = "0"
-which = sys.argv[1:] or ["1", "2", "2d", "3", "4", "5", "mp", "gray", "refbench"]
+which = sys.argv[1:] or ["1", "2", "2d", "3", "4", "5", "mp", "gray", "cam", "refbench"]
 rng = np.random.default_rng(0)
 if "1" in which:
     h = Hologram(rng.random((512, 512), dtype=np.float32), phase=rng.uniform(-3, 3, (512, 512)).astype(np.float32))
@@ -103,6 +103,22 @@ if "gray" in which:
         p = h.get_phase()
     t2 = time.perf_counter()
     print(f"get_phase_gray(8) 1152x1920: {(t1-t0)*100:.3f} ms per call ({g.nbytes/1e6:.1f} MB down) vs get_phase() {(t2-t1)*100:.3f} ms ({p.nbytes/1e6:.1f} MB down)")
+if "cam" in which:
+    from slmsuite_b200 import SimulatedCamera
+
+    slm = (1024, 1024)
+    yy, xx = np.mgrid[0:1200, 0:1600]
+    knm = np.array([424.0 + yy * 1.0, 224.0 + xx * 1.0]) + 0.25
+    cam = SimulatedCamera(slm, resolution=(1600, 1200), knm_cam=knm, shape_padded=(2048, 2048), bitdepth=8)
+    cam.set_exposure(1e4)
+    disp = rng.integers(0, 256, slm).astype(np.uint8)
+    cam.get_image(disp, 256)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        img = cam.get_image(disp, 256)
+    t1 = time.perf_counter()
+    print(f"SimulatedCamera 1600x1200 of a 1024^2 SLM in 2048^2: {(t1-t0)*100:.3f} ms per get_image "
+          f"(4 MB phase up, forward transform, sampling, {img.nbytes/1e6:.1f} MB image down)")
 if "refbench" in which:
     # the reference's own benchmark: tests/holography/test_algorithms.py:121-145 (1024^2, 20 spots, 20 iterations)
     for method in ("GS", "WGS-Leonardo", "WGS-Kim", "WGS-Nogrette"):

@@ -190,6 +190,36 @@ SLMGS_API int slmgs_launch_geometry(const slmgs_ctx*, int* out4);
  * which: 0 = row fused, 1 = column fused (GS), 2 = row first, 3 = column forward (populate). ms_out = average ms per launch */
 SLMGS_API int slmgs_time_kernel(slmgs_ctx*, int which, int n, float* ms_out);
 
+/* ---- compressed spot hologram ("next" row) --------------------------------------------
+ * CompressedSpotHologram, slmsuite/holography/algorithms/_spots.py:178-1019: instead of a DFT grid every spot n owns a
+ * phase kernel phi_n(pix) = sum_d spot_zernike[d, n] Z_d(x_pix, y_pix) (_spots.py:595-636) and the maps of the GS loop
+ * are direct sums over pixels / spots (the reference's NumPy matmul pair :767-824 / :887-915 and its CUDA pair
+ * toolbox/cuda.cu:95-288).  The host expands the Zernike basis into monomials: mono[m][pix] = x^px y^py (float64,
+ * aperture-scaled grid) and cw[m][n] = sum_d c[m, d] spot_zernike[d, n] (float64, radians), at most 10 monomials.
+ * Targets / weights / far field are N-vectors; the target may hold NaN (MRAF noise point) and 0 (null point).
+ * slmgs_params as for slmgs_run (feedback is always the computed spot amplitude, _spots.py:950-989). */
+typedef struct slmgs_comp slmgs_comp;
+SLMGS_API const char* slmgs_comp_last_error(const slmgs_comp*);
+SLMGS_API int slmgs_comp_create(slmgs_comp** out, int device, int h, int w, int n_spots, int n_monomials);
+SLMGS_API int slmgs_comp_destroy(slmgs_comp*);
+SLMGS_API int slmgs_comp_sync(slmgs_comp*);
+SLMGS_API long long slmgs_comp_launch_count(const slmgs_comp*);
+SLMGS_API int slmgs_comp_set_basis(slmgs_comp*, const double* mono, const double* cw);   /* _build_cupy_kernel_batched, :595-636 */
+SLMGS_API int slmgs_comp_set_phase(slmgs_comp*, const float* phase);                     /* [h][w] */
+SLMGS_API int slmgs_comp_get_phase(slmgs_comp*, float* phase);
+SLMGS_API int slmgs_comp_set_amp_scalar(slmgs_comp*, float amp);
+SLMGS_API int slmgs_comp_set_amp_array(slmgs_comp*, const float* amp);                   /* [h][w] */
+SLMGS_API int slmgs_comp_set_target(slmgs_comp*, const float* target);                   /* [N], set_target :917-948 */
+SLMGS_API int slmgs_comp_set_weights(slmgs_comp*, const float* weights);
+SLMGS_API int slmgs_comp_get_weights(slmgs_comp*, float* weights);
+SLMGS_API int slmgs_comp_set_phase_ff(slmgs_comp*, const float* phase_ff);
+SLMGS_API int slmgs_comp_get_phase_ff(slmgs_comp*, float* phase_ff);
+SLMGS_API int slmgs_comp_get_amp_ff(slmgs_comp*, float* amp_ff);
+SLMGS_API int slmgs_comp_get_farfield(slmgs_comp*, float* farfield_c64);                 /* [N] interleaved re/im, normalised (:822) */
+SLMGS_API int slmgs_comp_forward(slmgs_comp*, int populate);                              /* _nearfield2farfield :677-708 + amp_ff; populate: also phase_ff (_populate_results) */
+SLMGS_API int slmgs_comp_run(slmgs_comp*, const slmgs_params* params, int n_iter, int populate); /* optimize_gs with the compressed maps */
+SLMGS_API int slmgs_comp_timer(slmgs_comp*, int start, float* ms);                        /* CUDA events on the context's stream */
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,6 +104,27 @@ SIGNATURES = {
     "slmgs_launch_count": (C.c_longlong, [_ctx]),
     "slmgs_launch_geometry": (C.c_int, [_ctx, _ip]),
     "slmgs_time_kernel": (C.c_int, [_ctx, C.c_int, C.c_int, _fp]),
+    # compressed spot hologram
+    "slmgs_comp_last_error": (C.c_char_p, [_ctx]),
+    "slmgs_comp_create": (C.c_int, [C.POINTER(_ctx), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "slmgs_comp_destroy": (C.c_int, [_ctx]),
+    "slmgs_comp_sync": (C.c_int, [_ctx]),
+    "slmgs_comp_launch_count": (C.c_longlong, [_ctx]),
+    "slmgs_comp_set_basis": (C.c_int, [_ctx, _dp, _dp]),
+    "slmgs_comp_set_phase": (C.c_int, [_ctx, _fp]),
+    "slmgs_comp_get_phase": (C.c_int, [_ctx, _fp]),
+    "slmgs_comp_set_amp_scalar": (C.c_int, [_ctx, C.c_float]),
+    "slmgs_comp_set_amp_array": (C.c_int, [_ctx, _fp]),
+    "slmgs_comp_set_target": (C.c_int, [_ctx, _fp]),
+    "slmgs_comp_set_weights": (C.c_int, [_ctx, _fp]),
+    "slmgs_comp_get_weights": (C.c_int, [_ctx, _fp]),
+    "slmgs_comp_set_phase_ff": (C.c_int, [_ctx, _fp]),
+    "slmgs_comp_get_phase_ff": (C.c_int, [_ctx, _fp]),
+    "slmgs_comp_get_amp_ff": (C.c_int, [_ctx, _fp]),
+    "slmgs_comp_get_farfield": (C.c_int, [_ctx, _fp]),
+    "slmgs_comp_forward": (C.c_int, [_ctx, C.c_int]),
+    "slmgs_comp_run": (C.c_int, [_ctx, _pp, C.c_int, C.c_int]),
+    "slmgs_comp_timer": (C.c_int, [_ctx, C.c_int, _fp]),
 }
 
 

@@ -1457,3 +1457,270 @@ extern "C" int slmgs_profile_read(slmgs_ctx* c, float* ms6, int* count6) {
 #endif
     return SLMGS_OK;
 }
+
+// ==========================================================================================
+// CompressedSpotHologram ("next" row 4): include/slmgs.h "compressed spot hologram"
+// ==========================================================================================
+#include "slmgs_compressed.h"
+
+struct slmgs_comp {
+    int device, h, w, N, M, MT;
+    long long S;
+    rt_stream stream;
+    std::string err;
+    long long launches;
+    int sms;
+    double *mono, *cw, *facc;
+    float *phase, *amp, *target, *weights, *amp_ff, *phase_ff;
+    cf *nf, *far, *far_norm;
+    float amp_scalar;
+};
+
+static std::string g_comp_error;
+static int cfail(slmgs_comp* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    else g_comp_error = msg;
+    return code;
+}
+static int crt(slmgs_comp* c, int e, const char* what) {
+    if (e == 0) return 0;
+    return cfail(c, rt_is_oom(e) ? SLMGS_ERR_OOM : SLMGS_ERR_CUDA, std::string(what) + ": " + rt_errstr(e));
+}
+#define CRT(c, call)                                \
+    do {                                            \
+        int e__ = crt((c), (call), #call);          \
+        if (e__) return e__;                        \
+    } while (0)
+#define CHECK_COMP(c) \
+    if (!(c)) return SLMGS_ERR_INVALID; \
+    CRT(c, rt_set_device((c)->device))
+
+extern "C" const char* slmgs_comp_last_error(const slmgs_comp* c) { return c ? c->err.c_str() : g_comp_error.c_str(); }
+
+extern "C" int slmgs_comp_destroy(slmgs_comp* c) {
+    if (!c) return SLMGS_OK;
+    rt_set_device(c->device);
+    if (c->stream) rt_sync(c->stream);
+    void* ptrs[] = {c->mono, c->cw, c->facc, c->phase, c->amp, c->target, c->weights, c->amp_ff, c->phase_ff,
+                    c->nf, c->far, c->far_norm};
+    for (void* p : ptrs)
+        if (p) rt_free(p);
+    if (c->stream) rt_stream_destroy(c->stream);
+    delete c;
+    return SLMGS_OK;
+}
+
+extern "C" int slmgs_comp_create(slmgs_comp** out, int device, int h, int w, int n_spots, int n_monomials) {
+    if (!out) return cfail(nullptr, SLMGS_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (h < 1 || w < 1 || n_spots < 1) return cfail(nullptr, SLMGS_ERR_INVALID, "slm_shape and the number of spots must be positive");
+    if (n_monomials < 1 || n_monomials > 10)
+        return cfail(nullptr, SLMGS_ERR_INVALID, "the Zernike basis must expand into 1..10 monomials (up to third order)");
+    int e = rt_set_device(device);
+    if (e) return cfail(nullptr, SLMGS_ERR_CUDA, std::string("cudaSetDevice: ") + rt_errstr(e));
+    slmgs_comp* c = new slmgs_comp();
+    c->device = device; c->h = h; c->w = w; c->N = n_spots; c->M = n_monomials;
+    c->MT = n_monomials <= 2 ? 2 : n_monomials <= 6 ? 6 : 10;
+    c->S = (long long)h * w;
+    c->launches = 0;
+    c->sms = rt_sm_count();
+    c->stream = nullptr;
+    c->amp_scalar = (float)(1.0 / sqrt((double)c->S));
+    c->mono = c->cw = c->facc = nullptr;
+    c->phase = c->amp = c->target = c->weights = c->amp_ff = c->phase_ff = nullptr;
+    c->nf = c->far = c->far_norm = nullptr;
+    const size_t S = (size_t)c->S, N = (size_t)n_spots;
+    int err = 0;
+    void* p;
+#define CA(field, type, count)                                                              \
+    if (!err) {                                                                             \
+        err = rt_malloc(&p, (count) * sizeof(type));                                        \
+        if (!err) { c->field = (type*)p; err = rt_memset(p, 0, (count) * sizeof(type), nullptr); } \
+    }
+    err = rt_stream_create(&c->stream);
+    CA(mono, double, (size_t)c->MT * S)
+    CA(cw, double, (size_t)c->MT * N)
+    CA(facc, double, 2 * N)
+    CA(phase, float, S)
+    CA(target, float, N)
+    CA(weights, float, N)
+    CA(amp_ff, float, N)
+    CA(phase_ff, float, N)
+    CA(nf, cf, S)
+    CA(far, cf, N)
+    CA(far_norm, cf, N)
+#undef CA
+    if (!err) err = rt_sync(nullptr);
+    if (err) {
+        g_comp_error = std::string("compressed context allocation: ") + rt_errstr(err);
+        const int code = rt_is_oom(err) ? SLMGS_ERR_OOM : SLMGS_ERR_CUDA;
+        slmgs_comp_destroy(c);
+        return code;
+    }
+    *out = c;
+    return SLMGS_OK;
+}
+
+extern "C" int slmgs_comp_sync(slmgs_comp* c) {
+    CHECK_COMP(c);
+    CRT(c, rt_sync(c->stream));
+    return SLMGS_OK;
+}
+extern "C" long long slmgs_comp_launch_count(const slmgs_comp* c) { return c ? c->launches : 0; }
+
+// mono: [M][h*w] float64 monomial values; cw: [M][N] float64 per-spot monomial weights in RADIANS
+extern "C" int slmgs_comp_set_basis(slmgs_comp* c, const double* mono, const double* cw) {
+    CHECK_COMP(c);
+    if (!mono || !cw) return cfail(c, SLMGS_ERR_INVALID, "mono / cw is NULL");
+    CRT(c, rt_h2d(c->mono, mono, (size_t)c->M * c->S * sizeof(double), c->stream));
+    std::vector<double> turns((size_t)c->M * c->N);
+    const double inv = 1.0 / 6.283185307179586476925286766559;
+    for (size_t i = 0; i < turns.size(); ++i) turns[i] = cw[i] * inv;
+    CRT(c, rt_h2d(c->cw, turns.data(), turns.size() * sizeof(double), c->stream));
+    return SLMGS_OK;
+}
+extern "C" int slmgs_comp_set_phase(slmgs_comp* c, const float* phase) {
+    CHECK_COMP(c);
+    if (!phase) return cfail(c, SLMGS_ERR_INVALID, "phase is NULL");
+    CRT(c, rt_h2d(c->phase, phase, (size_t)c->S * sizeof(float), c->stream));
+    return SLMGS_OK;
+}
+extern "C" int slmgs_comp_get_phase(slmgs_comp* c, float* phase) {
+    CHECK_COMP(c);
+    if (!phase) return cfail(c, SLMGS_ERR_INVALID, "phase is NULL");
+    CRT(c, rt_d2h(phase, c->phase, (size_t)c->S * sizeof(float), c->stream));
+    return SLMGS_OK;
+}
+extern "C" int slmgs_comp_set_amp_scalar(slmgs_comp* c, float amp) {
+    CHECK_COMP(c);
+    if (c->amp) { CRT(c, rt_sync(c->stream)); rt_free(c->amp); c->amp = nullptr; }
+    c->amp_scalar = amp;
+    return SLMGS_OK;
+}
+extern "C" int slmgs_comp_set_amp_array(slmgs_comp* c, const float* amp) {
+    CHECK_COMP(c);
+    if (!amp) return cfail(c, SLMGS_ERR_INVALID, "amp is NULL");
+    if (!c->amp) {
+        void* p = nullptr;
+        CRT(c, rt_malloc(&p, (size_t)c->S * sizeof(float)));
+        c->amp = (float*)p;
+    }
+    CRT(c, rt_h2d(c->amp, amp, (size_t)c->S * sizeof(float), c->stream));
+    return SLMGS_OK;
+}
+#define COMP_VEC_SETTER(name, field)                                                          \
+    extern "C" int slmgs_comp_set_##name(slmgs_comp* c, const float* v) {                     \
+        CHECK_COMP(c);                                                                        \
+        if (!v) return cfail(c, SLMGS_ERR_INVALID, #name " is NULL");                         \
+        CRT(c, rt_h2d(c->field, v, (size_t)c->N * sizeof(float), c->stream));                 \
+        return SLMGS_OK;                                                                      \
+    }
+#define COMP_VEC_GETTER(name, field, type)                                                    \
+    extern "C" int slmgs_comp_get_##name(slmgs_comp* c, float* v) {                           \
+        CHECK_COMP(c);                                                                        \
+        if (!v) return cfail(c, SLMGS_ERR_INVALID, #name " is NULL");                         \
+        CRT(c, rt_d2h(v, c->field, (size_t)c->N * sizeof(type), c->stream));                  \
+        return SLMGS_OK;                                                                      \
+    }
+COMP_VEC_SETTER(target, target)
+COMP_VEC_SETTER(weights, weights)
+COMP_VEC_SETTER(phase_ff, phase_ff)
+COMP_VEC_GETTER(weights, weights, float)
+COMP_VEC_GETTER(amp_ff, amp_ff, float)
+COMP_VEC_GETTER(phase_ff, phase_ff, float)
+COMP_VEC_GETTER(farfield, far_norm, cf)
+
+static CompArgs comp_args(slmgs_comp* c) {
+    CompArgs a;
+    memset(&a, 0, sizeof a);
+    a.S = c->S; a.N = c->N; a.M = c->M;
+    a.mono = c->mono; a.cw = c->cw; a.phase = c->phase; a.amp = c->amp; a.amp_scalar = c->amp_scalar;
+    a.nf = c->nf; a.facc = c->facc; a.far = c->far; a.phase_out = c->phase;
+    return a;
+}
+template <template <int> class K> static int comp_launch_mt(slmgs_comp* c, int gx, int gy, const CompArgs& a) {
+    c->launches++;
+    if (c->MT == 2) return launch_kernel<K<2>>(gx, gy, 256, 0, c->stream, a);
+    if (c->MT == 6) return launch_kernel<K<6>>(gx, gy, 256, 0, c->stream, a);
+    return launch_kernel<K<10>>(gx, gy, 256, 0, c->stream, a);
+}
+// nearfield -> farfield accumulators (un-normalised sums in facc)
+static int comp_near2far(slmgs_comp* c) {
+    CompArgs a = comp_args(c);
+    long long blocks = (c->S + 255) / 256;
+    if (blocks > (long long)c->sms * 8) blocks = (long long)c->sms * 8;
+    c->launches++;
+    CRT(c, launch_kernel<CompBuildKernel>((int)blocks, 1, 256, 0, c->stream, a));
+    const int gy = (c->N + COMP_SPOTS - 1) / COMP_SPOTS;
+    const long long span = 256LL * COMP_PPT;
+    long long gx = (c->S + span - 1) / span;
+    // enough blocks to fill the GPU a few times over, few enough that every spot sees O(100) atomic adds per block row
+    long long want = ((long long)c->sms * 4 + gy - 1) / gy;
+    if (want < 1) want = 1;
+    if (gx > want) gx = want;
+    CRT(c, comp_launch_mt<CompNear2FarKernel>(c, (int)gx, gy, a));
+    return SLMGS_OK;
+}
+static int comp_vec(slmgs_comp* c, const slmgs_params* p, int finalize) {
+    CompVecArgs v;
+    memset(&v, 0, sizeof v);
+    v.facc = c->facc; v.far_norm = c->far_norm; v.far = c->far; v.amp_ff = c->amp_ff; v.phase_ff = c->phase_ff;
+    v.weights = c->weights; v.target = c->target; v.N = c->N; v.finalize = finalize;
+    v.wgs.method = METHOD_GS; v.wgs.inv_fnorm = 1.f; v.wgs.neg_inv_mean = -1.f;
+    if (p) {
+        v.update = p->update_weights; v.phase_mode = p->phase_mode; v.mraf = p->mraf;
+        v.mraf_has_factor = p->mraf_has_factor; v.mraf_factor = p->mraf_factor;
+        v.wgs.method = p->method; v.wgs.p = p->feedback_exponent; v.wgs.f = p->feedback_factor;
+    }
+    c->launches++;
+    CRT(c, launch_kernel<CompVecKernel>(1, 1, 1024, (1024 + 8) * sizeof(double), c->stream, v));
+    return SLMGS_OK;
+}
+
+// _nearfield2farfield + _midloop_cleaning (+ phase_ff = angle(farfield), _populate_results :934-949)
+extern "C" int slmgs_comp_forward(slmgs_comp* c, int populate) {
+    CHECK_COMP(c);
+    int e;
+    if ((e = comp_near2far(c))) return e;
+    return comp_vec(c, nullptr, populate ? 2 : 1);
+}
+
+// optimize_gs for the compressed maps: n_iter iterations (+ _populate_results)
+extern "C" int slmgs_comp_run(slmgs_comp* c, const slmgs_params* params, int n_iter, int populate) {
+    CHECK_COMP(c);
+    if (n_iter < 0) return cfail(c, SLMGS_ERR_INVALID, "n_iter < 0");
+    if (n_iter > 0 && !params) return cfail(c, SLMGS_ERR_INVALID, "params is NULL");
+    for (int i = 0; i < n_iter; ++i) {
+        const slmgs_params* p = params + i;
+        if (p->method < SLMGS_GS || p->method > SLMGS_WGS_TANH) return cfail(c, SLMGS_ERR_INVALID, "unknown method");
+        if (p->phase_mode < 0 || p->phase_mode > 2) return cfail(c, SLMGS_ERR_INVALID, "unknown phase_mode");
+        if (p->update_weights && p->method == SLMGS_GS) return cfail(c, SLMGS_ERR_INVALID, "GS has no weight update");
+        if (p->mraf && p->zero_weights) return cfail(c, SLMGS_ERR_INVALID, "the MRAF zero_factor accumulator is not supported for compressed holograms");
+    }
+    int e;
+    for (int i = 0; i < n_iter; ++i) {
+        if ((e = comp_near2far(c))) return e;
+        if ((e = comp_vec(c, params + i, 0))) return e;
+        CompArgs a = comp_args(c);
+        const long long span = 256LL * COMP_PPT;
+        CRT(c, comp_launch_mt<CompFar2NearKernel>(c, (int)((c->S + span - 1) / span), 1, a));
+    }
+    if (populate) return slmgs_comp_forward(c, 1);
+    return SLMGS_OK;
+}
+
+extern "C" int slmgs_comp_timer(slmgs_comp* c, int start, float* ms) {
+    CHECK_COMP(c);
+#ifndef SLMGS_EMULATE
+    static thread_local cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (!e0) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
+    if (start) return (int)cudaEventRecord(e0, c->stream) ? SLMGS_ERR_CUDA : SLMGS_OK;
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    if (ms) cudaEventElapsedTime(ms, e0, e1);
+#else
+    if (ms) *ms = 0.f;
+    (void)start;
+#endif
+    return SLMGS_OK;
+}

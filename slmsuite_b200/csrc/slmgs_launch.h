@@ -60,7 +60,15 @@ SLMGS_DEVICE void run_phases(typename K::State& st, const typename K::Args& a, c
     }
 }
 
-template <class K> __global__ void __launch_bounds__(K::MAXT, 1) slmgs_kernel(const typename K::Args a) {
+// optional K::MINB: minimum resident blocks per SM (register cap), default 1
+template <class K, class = void> struct min_blocks {
+    static constexpr int value = 1;
+};
+template <class K> struct min_blocks<K, decltype((void)K::MINB)> {
+    static constexpr int value = K::MINB;
+};
+
+template <class K> __global__ void __launch_bounds__(K::MAXT, min_blocks<K>::value) slmgs_kernel(const typename K::Args a) {
     extern __shared__ __align__(16) unsigned char slmgs_smem_raw[];
     cf* smem = reinterpret_cast<cf*>(slmgs_smem_raw);
     typename K::State st;

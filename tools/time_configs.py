@@ -40,7 +40,7 @@ def tag(h):
 if "--dense" in sys.argv:  # force the dense loop (every column tile processed)
     sys.argv.remove("--dense")
     os.environ["SLMGS_SPARSE"] = "0"
-which = sys.argv[1:] or ["1", "2", "2d", "3", "4", "5", "mp", "gray", "cam", "refbench"]
+which = sys.argv[1:] or ["1", "2", "2d", "3", "4", "5", "mp", "gray", "cam", "comp", "refbench"]
 rng = np.random.default_rng(0)
 if "1" in which:
     h = Hologram(rng.random((512, 512), dtype=np.float32), phase=rng.uniform(-3, 3, (512, 512)).astype(np.float32))
@@ -119,6 +119,29 @@ if "cam" in which:
     t1 = time.perf_counter()
     print(f"SimulatedCamera 1600x1200 of a 1024^2 SLM in 2048^2: {(t1-t0)*100:.3f} ms per get_image "
           f"(4 MB phase up, forward transform, sampling, {img.nbytes/1e6:.1f} MB image down)")
+if "comp" in which:
+    from slmsuite_b200 import CompressedSpotHologram
+
+    slm = (1152, 1920)
+    yy, xx = np.mgrid[0:slm[0], 0:slm[1]]
+    grid = ((xx - slm[1] / 2) * 12.6, (yy - slm[0] / 2) * 12.6)   # x / lambda for an 8 um pitch at 633 nm
+    scaling = 1.0 / (2 * 6000.0)
+    for dim, n_spots in ((2, 1000), (3, 1000), (2, 100)):
+        v = rng.uniform(-0.03, 0.03, (dim, n_spots))
+        if dim == 3:
+            v[2] = rng.uniform(-1e-5, 1e-5, n_spots)
+        h = CompressedSpotHologram(v, basis="kxy", slm_grid=grid, zernike_scaling=scaling,
+                                   phase=rng.uniform(-3, 3, slm).astype(np.float32))
+        h.optimize("WGS-Kim", maxiter=3, verbose=False)
+        ms = C.c_float()
+        lib.slmgs_comp_sync(h._ctx)
+        lib.slmgs_comp_timer(h._ctx, 1, None)
+        h.optimize("WGS-Kim", maxiter=10, verbose=False)
+        lib.slmgs_comp_timer(h._ctx, 0, C.byref(ms))
+        pairs = 2 * 10.5 * n_spots * slm[0] * slm[1]   # two maps per iteration (+ the trailing forward map)
+        print(f"CompressedSpotHologram {n_spots} spots ({dim}-D) on a 1152x1920 SLM, WGS-Kim 10 it: {ms.value:.2f} ms -> "
+              f"{10/ms.value*1e3:.1f} it/s, {pairs/ms.value/1e9:.2f} T (pixel, spot) pairs/s; "
+              f"uniformity of |farfield|: {h.amp_ff.min()/h.amp_ff.max():.3f}")
 if "refbench" in which:
     # the reference's own benchmark: tests/holography/test_algorithms.py:121-145 (1024^2, 20 spots, 20 iterations)
     for method in ("GS", "WGS-Leonardo", "WGS-Kim", "WGS-Nogrette"):

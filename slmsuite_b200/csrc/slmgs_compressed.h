@@ -42,7 +42,10 @@ struct CompArgs {
 
 #if defined(__CUDACC__) && !defined(SLMGS_EMULATE)
 SLMGS_DEVICE void sincos_turns(double turns, float* s, float* c) {
-    const double t = turns - rint(turns);  // [-0.5, 0.5]
+    // round to nearest integer with two FP64 adds (|turns| < 2^51) instead of FRND.F64, which shares the 16-lane XU
+    // pipe with the two MUFU evaluations and the F2F below -- the unit that bounds these kernels
+    const double r = (turns + 6755399441055744.0) - 6755399441055744.0;
+    const double t = turns - r;  // [-0.5, 0.5]
     // MUFU sine / cosine on an argument already reduced to [-pi, pi]: absolute error 2^-21.4 (CUDA programming guide),
     // the size of one float32 rounding of the result; the reduction above is where the accuracy comes from
     __sincosf(6.283185307179586f * (float)t, s, c);

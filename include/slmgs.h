@@ -133,8 +133,8 @@ SLMGS_API int slmgs_run(slmgs_ctx*, const slmgs_params* params, int n_iter, int 
  * weights (no MRAF noise pixel, no spot-feedback window) are skipped by the column kernels and their columns are
  * neither stored nor loaded by the row kernels: identical results, several times faster on spot targets (the
  * motivation of the reference's CompressedSpotHologram, _spots.py:222-241).  The occupancy is recomputed on the
- * device after every target / weights upload.  slmgs_sparse_info: out[0] = last slmgs_run was sparse,
- * out[1] = active column tiles, out[2] = column tiles. */
+ * device after every target / weights upload, per hologram of a batch.  slmgs_sparse_info: out[0] = last slmgs_run
+ * was sparse, out[1] = active column tiles (of the hologram with the most), out[2] = column tiles. */
 SLMGS_API int slmgs_set_sparse(slmgs_ctx*, int mode);
 SLMGS_API int slmgs_sparse_info(const slmgs_ctx*, int* out3);
 

@@ -145,7 +145,9 @@ struct slmgs_ctx {
     std::vector<int> tile_flags_h; // host copy of tile_flags
     std::vector<int> spot_x_h;     // host copy of the spot x coordinates (window tiles)
     int tile_key;                  // (mraf, spot width) the device list was built for, -1 = none
-    int n_active;                  // tiles in tile_list
+    int* tile_count;               // device [B]: active tiles per hologram
+    int n_active;                  // most active tiles of any hologram (grid size of the sparse column kernels)
+    long long n_active_total;      // active tiles summed over the batch
     bool sparse_now;               // the launches being issued use the tile list
     // grow-only device scratch for small downloads (gray levels, camera images): cudaMalloc / cudaFree per call
     // cost milliseconds once the process holds gigabytes of allocations
@@ -324,7 +326,8 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
     c->zero_w = nullptr;
     c->sparse_mode = env_int("SLMGS_SPARSE", 1) != 0 ? 1 : 0;
     c->tiles_dirty = true;
-    c->tile_flags = nullptr; c->tile_list = nullptr; c->tile_byte = nullptr;
+    c->tile_flags = nullptr; c->tile_list = nullptr; c->tile_byte = nullptr; c->tile_count = nullptr;
+    c->n_active_total = 0;
     c->tile_key = -1;
     c->n_active = 0;
     c->sparse_now = false;
@@ -397,7 +400,7 @@ extern "C" int slmgs_destroy(slmgs_ctx* c) {
     void* ptrs[] = {c->fld, c->farfield, c->stage_c, c->stage_f, c->phase, c->amp, c->prop, c->target,
                     c->weights, c->phase_ff, c->amp_ff, c->twA_row, c->twB_row, c->twA_col, c->twB_col, c->acc,
                     c->partial, c->spot_x, c->spot_y, c->spot_amp, c->spot_pw, c->phase_saved, c->mp_sum, c->zero_w,
-                    c->tile_flags, c->tile_list, c->tile_byte, c->samp_y, c->samp_x, c->scratch};
+                    c->tile_flags, c->tile_list, c->tile_byte, c->tile_count, c->samp_y, c->samp_x, c->scratch};
     for (void* p : ptrs)
         if (p) rt_free(p);
 #ifndef SLMGS_EMULATE
@@ -665,6 +668,7 @@ static RowArgs row_args(slmgs_ctx* c) {
     a.pf_dist = c->prefetch ? c->sms * (c->row_threads <= 512 ? 2 : 1) : 0;
     if (c->sparse_now) {
         a.colflag = c->tile_byte;
+        a.colflag_bs = c->W / (c->col_threads / c->icol.tpl);
         a.ctile_shift = 0;
         while ((1 << a.ctile_shift) < c->col_threads / c->icol.tpl) ++a.ctile_shift;
         a.pf_dist = 0;
@@ -699,7 +703,11 @@ static ColArgs col_args(slmgs_ctx* c) {
     a.zero_factor = 1.0f;
     a.pdl = (c->use_pdl && !c->profiling) ? 1 : 0;
     a.pf_dist = c->prefetch ? c->sms * (c->col_threads <= 512 ? 2 : 1) : 0;
-    if (c->sparse_now) a.tiles = c->tile_list;
+    if (c->sparse_now) {
+        a.tiles = c->tile_list;
+        a.tile_count = c->tile_count;
+        a.tiles_bs = c->W / (c->col_threads / c->icol.tpl);
+    }
     return a;
 }
 // profiling: bracket a launch with events from a pool (class k: 0..2 row modes, 3..5 column modes)
@@ -805,58 +813,82 @@ static int prepare_sparse(slmgs_ctx* c, const slmgs_params* params, int n_iter) 
     }
     const int C = c->col_threads / c->icol.tpl;
     const int ntiles = c->W / C;
+    const size_t B = (size_t)c->B;
     if (ntiles < 4) return 0;
     int e;
     if (!c->tile_flags) {
-        if ((e = dev_alloc(c, &c->tile_flags, (size_t)ntiles))) return e;
-        if ((e = dev_alloc(c, &c->tile_list, (size_t)ntiles))) return e;
-        if ((e = dev_alloc(c, &c->tile_byte, (size_t)ntiles))) return e;
+        if ((e = dev_alloc(c, &c->tile_flags, B * ntiles))) return e;
+        if ((e = dev_alloc(c, &c->tile_list, B * ntiles))) return e;
+        if ((e = dev_alloc(c, &c->tile_byte, B * ntiles))) return e;
+        if ((e = dev_alloc(c, &c->tile_count, B))) return e;
         c->tiles_dirty = true;
     }
     if (c->tiles_dirty) {
-        RT(c, rt_memset(c->tile_flags, 0, (size_t)ntiles * sizeof(int), c->stream));
+        RT(c, rt_memset(c->tile_flags, 0, B * ntiles * sizeof(int), c->stream));
         TileArgs t;
         memset(&t, 0, sizeof t);
         t.weights = c->weights; t.target = c->target;
         t.img_bs = (long long)c->H * c->W; t.target_bs = c->target_shared ? 0 : t.img_bs;
         t.tile_elems = (long long)c->H * C;
         t.flags = c->tile_flags;
+        t.flags_bs = ntiles;
         c->launches++;
         RT(c, launch_kernel<TileFlagKernel>(ntiles, c->B, 256, 0, c->stream, t));
-        c->tile_flags_h.resize(ntiles);
-        RT(c, rt_d2h(c->tile_flags_h.data(), c->tile_flags, (size_t)ntiles * sizeof(int), c->stream));
+        c->tile_flags_h.resize(B * ntiles);
+        RT(c, rt_d2h(c->tile_flags_h.data(), c->tile_flags, B * ntiles * sizeof(int), c->stream));
         RT(c, rt_sync(c->stream));
         c->tiles_dirty = false;
         c->tile_key = -1;
     }
     const int key = mraf | (spot_width << 1);
     if (key != c->tile_key) {
-        std::vector<unsigned char> on(ntiles, 0);
-        for (int t = 0; t < ntiles; ++t) on[t] = (c->tile_flags_h[t] & (mraf ? 3 : 1)) ? 1 : 0;
+        // tiles under the analysis.take windows (SpotGatherKernel): x_n + floor(k - (w-1)/2), negative indices wrap;
+        // the spot list is shared by the batch
+        std::vector<unsigned char> win(ntiles, 0);
         if (spot_width > 0) {
-            // columns of the analysis.take windows (SpotGatherKernel): x_n + floor(k - (w-1)/2), negative indices wrap
             const int base = (spot_width & 1) ? -((spot_width - 1) / 2) : -(spot_width / 2);
             for (int x0 : c->spot_x_h)
                 for (int d = 0; d < spot_width; ++d) {
                     int x = x0 + base + d;
                     if (x < 0) x += c->W;
                     if (x >= c->W) continue;  // out of range: the gather would fault in the reference too
-                    on[((x + (c->W >> 1)) % c->W) / C] = 1;
+                    win[((x + (c->W >> 1)) % c->W) / C] = 1;
                 }
         }
-        std::vector<int> list;
-        for (int t = 0; t < ntiles; ++t)
-            if (on[t]) list.push_back(t);
-        c->n_active = (int)list.size();
+        std::vector<unsigned char> on(B * ntiles, 0);
+        std::vector<int> list(B * ntiles, 0), count(B, 0);
+        long long total = 0;
+        int most = 0;
+        for (size_t b = 0; b < B; ++b) {
+            int n = 0;
+            for (int t = 0; t < ntiles; ++t) {
+                const bool a = (c->tile_flags_h[b * ntiles + t] & (mraf ? 3 : 1)) || win[t];
+                on[b * ntiles + t] = a ? 1 : 0;
+                if (a) list[b * ntiles + n++] = t;
+            }
+            count[b] = n;
+            total += n;
+            if (n > most) most = n;
+        }
+        c->n_active = most;
+        c->n_active_total = total;
         c->tile_key = key;
-        if (c->n_active > 0) {
+        if (most > 0) {
             RT(c, rt_h2d(c->tile_list, list.data(), list.size() * sizeof(int), c->stream));
-            RT(c, rt_h2d(c->tile_byte, on.data(), (size_t)ntiles, c->stream));
-            RT(c, rt_sync(c->stream));  // the host vectors go out of scope
+            RT(c, rt_h2d(c->tile_byte, on.data(), on.size(), c->stream));
+            RT(c, rt_h2d(c->tile_count, count.data(), count.size() * sizeof(int), c->stream));
         }
     }
-    // worthwhile below half occupancy (the filtered row kernel costs a little more per element than the dense one)
-    c->sparse_now = c->n_active > 0 && 2 * c->n_active <= ntiles;
+    // worthwhile below half occupancy (the filtered row kernel costs a little more per element than the dense one);
+    // every hologram needs at least one active tile (an empty one would leave stale columns in its field)
+    c->sparse_now = c->n_active > 0 && 2 * c->n_active_total <= (long long)B * ntiles;
+    if (c->sparse_now) {
+        for (size_t b = 0; b < B && c->sparse_now; ++b) {
+            bool any = false;
+            for (int t = 0; t < ntiles && !any; ++t) any = (c->tile_flags_h[b * ntiles + t] & (mraf ? 3 : 1)) != 0;
+            if (!any && spot_width == 0) c->sparse_now = false;
+        }
+    }
     return 0;
 }
 

@@ -171,6 +171,7 @@ struct RowArgs {
     int zero_bs;
     int pdl;             // launch with programmatic dependent launch
     int pf_dist;         // L2 prefetch distance in tiles (blocks resident on the GPU), 0 = off
+    long long colflag_bs;          // per-hologram stride of colflag
     const unsigned char* colflag;  // sparse far field: one byte per column tile of the column kernel (1 = the tile is
                                    // processed by the column kernel); columns of other tiles are identically zero after
                                    // the far-field constraint, so they are neither stored nor loaded.  nullptr = dense
@@ -207,8 +208,10 @@ template <int N, int MODE, bool STORE = false, bool SPARSE = false> struct RowKe
         int lt, sr, fr;  // thread-in-line, SLM row (may be >= h: idle), field row
         cf* s;           // shared-memory line base
         long long fbase, pbase;
+        long long cbase;  // this hologram's offset into colflag
         bool active;
     };
+    static SLMGS_DEVICE long long id_by_off(const Args&, const Loc& L) { return L.cbase; }
     static SLMGS_DEVICE Loc locate(const Args& a, cf* smem, const ThreadId& id) {
         Loc L;
         const int line = id.tid / F::TPL;
@@ -220,6 +223,7 @@ template <int N, int MODE, bool STORE = false, bool SPARSE = false> struct RowKe
         L.s = smem + (size_t)line * F::PADN;
         L.fbase = (long long)id.by * a.fld_bs + (long long)L.fr * a.W;
         L.pbase = (long long)id.by * a.phase_bs + (long long)L.sr * a.w;
+        L.cbase = (long long)id.by * a.colflag_bs;
         return L;
     }
     // SLM column of rolled x index n, or -1 outside the SLM
@@ -240,7 +244,7 @@ template <int N, int MODE, bool STORE = false, bool SPARSE = false> struct RowKe
             for (int m = 0; m < R; ++m) {
                 const int k = F::last_index(L.lt + F::TPL * u, m);
                 bool on = L.active;
-                if (SPARSE) on = on && __ldg(a.colflag + (k >> a.ctile_shift)) != 0;
+                if (SPARSE) on = on && __ldg(a.colflag + id_by_off(a, L) + (k >> a.ctile_shift)) != 0;
                 st.v[u * R + m] = on ? ld_stream(a.fld + L.fbase + k) : cmake(0.f, 0.f);
             }
         }
@@ -253,7 +257,7 @@ template <int N, int MODE, bool STORE = false, bool SPARSE = false> struct RowKe
             SLMGS_UNROLL
             for (int m = 0; m < R; ++m) {
                 const int k = F::last_index(L.lt + F::TPL * u, m);
-                if (SPARSE && __ldg(a.colflag + (k >> a.ctile_shift)) == 0) continue;
+                if (SPARSE && __ldg(a.colflag + id_by_off(a, L) + (k >> a.ctile_shift)) == 0) continue;
                 a.fld[L.fbase + k] = st.v[u * R + m];
             }
         }
@@ -411,7 +415,9 @@ struct ColArgs {
     int pdl;              // launch with programmatic dependent launch
     int pf_dist;          // L2 prefetch distance in tiles (blocks resident on the GPU), 0 = off
     const int* tiles;     // sparse far field: blockIdx.x -> column tile (only tiles whose constrained far field can be
-                          // non-zero are launched), or nullptr = every tile, in order
+                          // non-zero are launched), or nullptr = every tile, in order.  [B][tiles_bs]
+    const int* tile_count;  // [B] active tiles of each hologram: blocks with blockIdx.x >= count exit at once
+    int tiles_bs;
 };
 
 // CT: columns per tile known at compile time (block of MAXT threads), 0 = derived from blockDim at run time
@@ -431,6 +437,10 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
 #ifndef SLMGS_EMULATE
     static SLMGS_DEVICE void barrier(const ThreadId&) { __syncthreads(); }
 #endif
+    // sparse far field, batch: the grid is sized for the hologram with the most active tiles
+    static SLMGS_DEVICE bool skip(const Args& a, const ThreadId& id) {
+        return a.tiles != nullptr && id.bx >= __ldg(a.tile_count + id.by);
+    }
 
     struct Loc {
         int lt, col, C;  // thread-in-line, column inside the tile, columns per tile
@@ -443,7 +453,7 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
         L.C = CT > 0 ? CT : id.nthreads / F::TPL;  // a power of two
         L.col = id.tid & (L.C - 1);
         L.lt = id.tid >> ilog2(L.C);
-        const int tile = a.tiles ? __ldg(a.tiles + id.bx) : id.bx;
+        const int tile = a.tiles ? __ldg(a.tiles + (long long)id.by * a.tiles_bs + id.bx) : id.bx;
         L.gc = tile * L.C + L.col;
         L.s = smem + L.col;
         L.fbase = (long long)id.by * a.fld_bs + L.gc;

@@ -50,6 +50,14 @@ inline void accum_add(double* slot, double v) { *slot += v; }
 inline void atomic_add_double(double* slot, double v) { *slot += v; }
 #endif
 
+// optional K::skip(args, id): the whole block has nothing to do (evaluated once, before the first phase)
+template <class K, class = void> struct has_skip {
+    static constexpr bool value = false;
+};
+template <class K> struct has_skip<K, decltype((void)&K::skip)> {
+    static constexpr bool value = true;
+};
+
 #ifndef SLMGS_EMULATE
 template <class K, int P>
 SLMGS_DEVICE void run_phases(typename K::State& st, const typename K::Args& a, cf* smem, const ThreadId& id) {
@@ -83,6 +91,9 @@ template <class K> __global__ void __launch_bounds__(K::MAXT, min_blocks<K>::val
     // flushed (wait).  Both are no-ops when the kernel is launched without the PDL attribute.
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if constexpr (has_skip<K>::value) {
+        if (K::skip(a, id)) return;
+    }
     run_phases<K, 0>(st, a, smem, id);
 }
 
@@ -138,6 +149,9 @@ int launch_kernel(int gx, int gy, int nthreads, size_t smem_bytes, void* /*strea
             id.bx = bx;
             id.by = by;
             id.gx = gx;
+            if constexpr (has_skip<K>::value) {
+                if (K::skip(a, id)) continue;
+            }
             emu_phases<K, 0>(st, a, smem.data(), id);
         }
     return 0;

@@ -319,7 +319,8 @@ struct TileArgs {
     const float* target;
     long long img_bs, target_bs;
     long long tile_elems;  // H * C
-    int* flags;            // [W / C], zeroed by the caller
+    int* flags;            // [B][flags_bs], zeroed by the caller
+    int flags_bs;          // W / C
 };
 
 #ifndef SLMGS_EMULATE
@@ -345,7 +346,7 @@ struct TileFlagKernel {
             if (!(wv == 0.0f)) f |= 1;
             if (tv != tv) f |= 2;
         }
-        if (f) atomic_or_int(a.flags + id.bx, f);
+        if (f) atomic_or_int(a.flags + (long long)id.by * a.flags_bs + id.bx, f);
     }
 };
 

@@ -145,3 +145,99 @@ def test_8192_config5_shape_runs(cuda):
     a = h.amp_ff.astype(np.float64)
     assert abs(np.sum(a * a) - 1) < 1e-5
     assert h.iter == 3
+
+
+def test_config2_sparse_equals_dense_at_full_size(cuda):
+    """BASELINE configs[1] with the 64-spot target: the sparse far-field path (64 of 2048 column tiles) and the
+    dense loop give the same result, 12 WGS-Kim iterations across the phase-fixing iteration."""
+    from slmsuite_b200 import Hologram
+
+    shape, slm = (4096, 4096), (1152, 1920)
+    target = _spots(shape, 64, 1)
+    phase = np.random.default_rng(4).uniform(-np.pi, np.pi, slm).astype(np.float32)
+    out = []
+    for sparse in (True, False):
+        h = Hologram(target, phase=phase, slm_shape=slm)
+        h.set_sparse(sparse)
+        h.optimize("WGS-Kim", maxiter=12, verbose=False, fix_phase_iteration=5)
+        out.append(h)
+    a, b = out
+    used, n_active, n_tiles = a.sparse_info()
+    assert used and n_active <= 64 and n_tiles == 2048
+    assert not b.sparse_info()[0]
+    assert rel_rmse(a.amp_ff, b.amp_ff) <= 2e-6
+    assert rel_rmse(a.weights, b.weights) <= 2e-6
+    dphi = np.angle(np.exp(1j * (a.phase.astype(np.float64) - b.phase.astype(np.float64))))
+    assert np.sqrt(np.mean(dphi ** 2)) <= 2e-5
+
+
+def test_config4_batch_sparse_per_hologram(cuda):
+    """BASELINE configs[3] shard (8 holograms of 2048^2, 100 spots each, GS): per-hologram tile lists vs the dense loop."""
+    from slmsuite_b200 import HologramBatch
+
+    B, shape = 8, (2048, 2048)
+    targets = np.stack([_spots(shape, 100, 100 + b) for b in range(B)])
+    phases = np.random.default_rng(5).uniform(-np.pi, np.pi, (B,) + shape).astype(np.float32)
+    res = []
+    for sparse in (True, False):
+        hb = HologramBatch(targets, phase=phases)
+        hb.set_sparse(sparse)
+        hb.optimize("GS", maxiter=5, verbose=False)
+        res.append(hb)
+    a, b = res
+    used, n_active, n_tiles = a.sparse_info()
+    assert used and n_active <= 100 and n_active < n_tiles // 2
+    assert rel_rmse(a.phase, b.phase) <= 1e-6
+    assert rel_rmse(a.amp_ff, b.amp_ff) <= 1e-6
+
+
+def test_compressed_500_spots_vs_oracle(cuda):
+    """CompressedSpotHologram at a size the oracle still holds in memory (500 spots on a 256x384 SLM, 3-D, WGS-Kim)."""
+    from oracle import compressed_oracle
+    from slmsuite_b200 import CompressedSpotHologram
+
+    rng = np.random.default_rng(6)
+    slm = (256, 384)
+    yy, xx = np.mgrid[0:slm[0], 0:slm[1]]
+    grid = ((xx - slm[1] / 2) * 12.6, (yy - slm[0] / 2) * 12.6)
+    v = rng.uniform(-0.03, 0.03, (3, 500))
+    v[2] = rng.uniform(-2e-5, 2e-5, 500)
+    phase = rng.uniform(-np.pi, np.pi, slm).astype(np.float32)
+    kw = dict(method="WGS-Kim", maxiter=6, verbose=False, fix_phase_iteration=3)
+    args = dict(basis="kxy", slm_grid=grid, zernike_scaling=1.0 / 3000.0, phase=phase)
+    a = CompressedSpotHologram(v, **args)
+    a.optimize(**kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        b = compressed_oracle.OracleCompressedSpotHologram(v, **args)
+        b.optimize(**kw)
+    assert rel_rmse(a.amp_ff, b.amp_ff) <= 1e-5
+    assert rel_rmse(a.weights, b.weights) <= 1e-5
+    assert a.flags["fixed_phase"] == b.flags["fixed_phase"] is True
+    dphi = np.angle(np.exp(1j * (a.phase.astype(np.float64) - b.phase.astype(np.float64))))
+    assert np.sqrt(np.mean(dphi ** 2)) <= 1e-4
+
+
+def test_camera_2048_vs_oracle(cuda):
+    """SimulatedCamera on a 1024^2 SLM in a 2048^2 far field, 1200x1600 camera with a rotated affine grid."""
+    from oracle import camera_oracle
+    from slmsuite_b200 import SimulatedCamera
+
+    rng = np.random.default_rng(7)
+    slm = (1024, 1024)
+    yy, xx = np.mgrid[0:1200, 0:1600].astype(np.float64)
+    c, s = np.cos(0.1), np.sin(0.1)
+    knm = np.array([1024 + 1.6 * (c * (yy - 600) - s * (xx - 800)), 1024 + 1.6 * (s * (yy - 600) + c * (xx - 800))])
+    display = rng.integers(0, 256, slm).astype(np.uint8)
+    cam = SimulatedCamera(slm, resolution=(1600, 1200), knm_cam=knm, shape_padded=(2048, 2048), bitdepth=12)
+    cam.set_exposure(2.0e5)
+    img = cam.get_image(display, 256)
+    phase = camera_oracle.phase_from_display(display, 256, np.zeros(slm))
+    gold, raw = camera_oracle.camera_image(phase, np.ones(slm), slm, (2048, 2048), (1200, 1600), knm, 2.0e5, 1, 12)
+    assert img.dtype == gold.dtype == np.uint16
+    mine = cam.get_farfield_intensity() * np.float32(2.0e5)
+    assert rel_rmse(mine, raw) <= 1e-5
+    assert np.array_equal(mine == 0, raw == 0) and (raw == 0).any() and (raw > 0).any()
+    diff = img.astype(np.int64) - gold.astype(np.int64)
+    near = np.abs(raw - np.rint(raw)) <= 1e-3 * np.maximum(raw, 1.0)
+    assert np.all(np.abs(diff) <= 1) and not np.any((diff != 0) & ~near)

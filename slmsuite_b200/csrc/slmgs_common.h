@@ -51,6 +51,12 @@ SLMGS_DEVICE float2 ld_stream(const float2* p) {
 }
 SLMGS_DEVICE void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 SLMGS_DEVICE void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// asynchronous 4-byte copy global -> shared (LDGSTS): no register is held while the load is in flight
+SLMGS_DEVICE void cp_async_f32(float* smem_dst, const float* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+SLMGS_DEVICE void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // cached (L1-allocating) load for data that was prefetched into L1
 SLMGS_DEVICE float ld_cached(const float* p) {
     float v;
@@ -62,6 +68,8 @@ inline float ld_stream(const float* p) { return *p; }
 inline float2 ld_stream(const float2* p) { return *p; }
 inline void prefetch_l2(const void*) {}
 inline void prefetch_l1(const void*) {}
+inline void cp_async_f32(float* smem_dst, const float* gsrc) { *smem_dst = *gsrc; }
+inline void cp_async_wait_all() {}
 inline float ld_cached(const float* p) { return *p; }
 #endif
 

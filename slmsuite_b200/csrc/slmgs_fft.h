@@ -199,6 +199,38 @@ template <int N> struct Fft {
             fwd_stage_u<S, U + 1>(v, lt, twA, twB, s, si);
         }
     }
+    // The last forward stage split in two, so that a caller can issue work between the shared-memory reads and the
+    // butterflies: fwd_last_load reads the elements, fwd_last_compute runs the butterflies on them.
+    template <int S, int U> static SLMGS_DEVICE void fwd_load_u(cf* v, int lt, const cf* s, int si) {
+        if constexpr (U < E / radix<S>()) {
+            load_elems<S, U, 0>(v, lt, s, si);
+            fwd_load_u<S, U + 1>(v, lt, s, si);
+        }
+    }
+    template <int S, int U> static SLMGS_DEVICE void fwd_compute_u(cf* v) {
+        if constexpr (U < E / radix<S>()) {
+            RegFFT<radix<S>()>::template run<1, 1>(v + U * radix<S>());
+            fwd_compute_u<S, U + 1>(v);
+        }
+    }
+    static SLMGS_DEVICE void fwd_last_load(cf* v, int lt, const cf* s, int si) {
+        static_assert(NS > 1, "needs an exchange stage");
+        fwd_load_u<NS - 1, 0>(v, lt, s, si);
+    }
+    static SLMGS_DEVICE void fwd_last_compute(cf* v) {
+        fwd_compute_u<NS - 1, 0>(v);
+        cf o[E];
+        unscramble_all<radix<NS - 1>(), 0>(v, o);
+        SLMGS_UNROLL
+        for (int i = 0; i < E; ++i) v[i] = o[i];
+    }
+    // Shared-memory slot (in cf units, before the column interleave) that the last forward stage read its element i
+    // from and that the first inverse stage will write its element i to: PRIVATE to the thread in between.
+    static SLMGS_HD int last_slot(int lt, int i) {
+        constexpr int R = radix<NS - 1>();
+        return sbase<NS - 1>(lt + TPL * (i / R)) + (i % R) * sstride<NS - 1>();
+    }
+
     template <int S> static SLMGS_DEVICE void fwd_stage(cf* v, int lt, const cf* twA, const cf* twB, cf* s, int si) {
         fwd_stage_u<S, 0>(v, lt, twA, twB, s, si);
         if constexpr (S == NS - 1) {

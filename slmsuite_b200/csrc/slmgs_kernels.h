@@ -540,6 +540,34 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
     // 5 gives +3 % on dense 4096^2 WGS-Kim and +1.5 % on the bench workload; small problems (launch bound) lose a
     // few percent to the extra instructions, so it is only compiled in for long columns.
     static constexpr int IMG_PF = (N >= 2048) ? SLMGS_IMG_PF : 0;
+#ifndef SLMGS_STAGE
+#define SLMGS_STAGE 0
+#endif
+    // EXPERIMENT, compiled out (measured slower on B200): staging of weights / target through the
+    // thread's PRIVATE exchange slots.  The 16 shared-memory slots a thread
+    // reads in the last forward stage are the ones it writes in the first inverse stage, and nobody else touches
+    // them in between: that window is exactly the fused constraint.  So right after its reads the thread fires
+    // 4-byte cp.async copies of its weights (low word of slot i) and target (high word) values; they land while the
+    // radix-16 butterflies run, hold no registers and need no extra shared memory or barrier.  (The register pipeline
+    // that remains for phase_ff covers two elements of latency; the ncu source view put 20 % of this kernel's
+    // warp-time in waits on these loads.)  Result: -7 % on the bench workload and on dense WGS-Kim: the 32 extra
+    // LDGSTS + 16 LDS per thread land on the shared-memory / L1 data pipe, which is the busier resource.
+    static constexpr bool STAGE = SLMGS_STAGE != 0 && MODE == COL_FUSED && NS > 1 && N >= 2048;
+    static SLMGS_DEVICE void stage_images(const Args& a, const Loc& L) {
+        if constexpr (STAGE) {
+            constexpr int R = F::last_radix();
+            const bool update = VAR == VAR_GENERAL ? (a.wgs_update != 0) : (VAR == VAR_POW || VAR == VAR_POW_STORED);
+            const bool need_t = update || (VAR == VAR_GENERAL && a.mraf != 0);
+            SLMGS_UNROLL
+            for (int i = 0; i < E; ++i) {
+                const int off = F::last_index(L.lt + F::TPL * (i / R), i % R) * L.C;
+                float* slot = reinterpret_cast<float*>(L.s + F::last_slot(L.lt, i) * L.C);
+                cp_async_f32(slot, a.weights + L.ibase + off);
+                if (need_t) cp_async_f32(slot + 1, a.target + L.tbase + off);
+            }
+        }
+    }
+
     // COL_FUSED: pull the image values of the first SLMGS_IMG_PF elements into L1 before the last forward stage,
     // whose butterflies then hide the DRAM latency (the constraint continues the prefetch at the same distance)
     static SLMGS_DEVICE void prefetch_images_head(const Args& a, const Loc& L) {
@@ -552,8 +580,8 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
             SLMGS_UNROLL
             for (int e = 0; e < PF && e < E; ++e) {
                 const int off = F::last_index(L.lt + F::TPL * (e / R), e % R) * L.C;
-                prefetch_l1(a.weights + L.ibase + off);
-                if (need_t) prefetch_l1(a.target + L.tbase + off);
+                if (!STAGE) prefetch_l1(a.weights + L.ibase + off);
+                if (!STAGE && need_t) prefetch_l1(a.target + L.tbase + off);
                 if (stored) prefetch_l1(a.phase_ff + L.ibase + off);
             }
         }
@@ -576,6 +604,7 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
         const float* SLMGS_RESTRICT pp = a.phase_ff + L.ibase;
         float wq[E], tq[E], pq[E];
         constexpr int AHEAD = 2;
+        if (STAGE && !SCALED) cp_async_wait_all();
         // L1 prefetch distance (elements) of the fused kernel's image loads: the register pipeline above only
         // covers AHEAD elements, a fraction of the DRAM latency; prefetch.global.L1 needs no registers
         constexpr int PF = SCALED ? 0 : IMG_PF;
@@ -583,13 +612,18 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
         for (int e = 0; e < E + AHEAD; ++e) {
             if (PF > 0 && e + PF - AHEAD < E && e >= AHEAD) {
                 const int off = F::last_index(L.lt + F::TPL * ((e + PF - AHEAD) / R), (e + PF - AHEAD) % R) * L.C;
-                prefetch_l1(wp + off);
-                if (need_t) prefetch_l1(tp + off);
+                if (!(STAGE && !SCALED)) prefetch_l1(wp + off);
+                if (!(STAGE && !SCALED) && need_t) prefetch_l1(tp + off);
                 if (stored) prefetch_l1(pp + off);
             }
             if (e < E) {  // issue the loads of element e
                 const int off = F::last_index(L.lt + F::TPL * (e / R), e % R) * L.C;
-                if (PF > 0) {
+                if (STAGE && !SCALED) {  // weights / target were staged in this thread's private exchange slots
+                    const cf wt = L.s[F::last_slot(L.lt, e) * L.C];
+                    wq[e] = wt.x;
+                    tq[e] = need_t ? wt.y : 1.0f;
+                    pq[e] = stored ? (PF > 0 ? ld_cached(pp + off) : ld_stream(pp + off)) : 0.0f;
+                } else if (PF > 0) {
                     wq[e] = ld_cached(wp + off);
                     tq[e] = need_t ? ld_cached(tp + off) : 1.0f;
                     pq[e] = stored ? ld_cached(pp + off) : 0.0f;
@@ -685,7 +719,13 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
                 F::template fwd_stage<P>(st.v, L.lt, a.twA, a.twB, L.s, L.C);
             } else if constexpr (P == NS - 1) {
                 prefetch_images_head(a, L);
-                F::template fwd_stage<NS - 1>(st.v, L.lt, a.twA, a.twB, L.s, L.C);
+                if constexpr (STAGE) {
+                    F::fwd_last_load(st.v, L.lt, L.s, L.C);
+                    stage_images(a, L);
+                    F::fwd_last_compute(st.v);
+                } else {
+                    F::template fwd_stage<NS - 1>(st.v, L.lt, a.twA, a.twB, L.s, L.C);
+                }
                 constrain<false>(st, a, id, L);
                 F::template inv_stage<NS - 1>(st.v, L.lt, a.twA, a.twB, L.s, L.C);
             } else {

@@ -161,3 +161,28 @@ def test_oracle_side_by_side_seeded(backend):
     assert rel_rmse(a.weights, b.weights) <= 1e-5
     assert a.flags["fixed_phase"] == b.flags["fixed_phase"]
     assert a.stats["flags"]["fixed_phase"] == b.stats["flags"]["fixed_phase"]
+
+
+@pytest.mark.parametrize("method,kw", [("GS", {}), ("WGS-Leonardo", {}), ("WGS-Kim", {"fix_phase_iteration": 2}),
+                                       ("WGS-Nogrette", {})])
+def test_long_columns_vs_oracle(method, kw, backend):
+    """Columns of 2048 points take the code paths reserved for long columns (L1 prefetch and private-slot staging of
+    the constraint's image loads, slmgs_kernels.h): a tall 2048 x 16 problem against the oracle."""
+    from oracle import gs_oracle
+    from slmsuite_b200 import Hologram
+
+    rng = np.random.default_rng(11)
+    shape, slm = (2048, 16), (700, 12)
+    target = np.zeros(shape, dtype=np.float32)
+    target[rng.integers(0, 2048, 40), rng.integers(0, 16, 40)] = rng.uniform(0.5, 1.5, 40)
+    phase = rng.uniform(-np.pi, np.pi, slm).astype(np.float32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = Hologram(target, phase=phase, slm_shape=slm)
+        a.optimize(method, maxiter=4, verbose=False, **kw)
+        b = gs_oracle.OracleHologram(target, phase=phase, slm_shape=slm)
+        b.optimize(method, maxiter=4, verbose=False, **kw)
+    assert rel_rmse(a.amp_ff, b.amp_ff) <= 1e-5
+    assert rel_rmse(a.weights, b.weights) <= 1e-5
+    dphi = np.angle(np.exp(1j * (a.phase.astype(np.float64) - b.phase.astype(np.float64))))
+    assert np.sqrt(np.mean(dphi ** 2)) <= 2e-5

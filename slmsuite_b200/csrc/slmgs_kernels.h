@@ -67,6 +67,22 @@ SLMGS_DEVICE float fast_pow(float x, float y) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y * l));
     return r;
 }
+SLMGS_DEVICE float fast_lg2(float x) {
+    float l;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+    return l;
+}
+SLMGS_DEVICE float fast_ex2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// flush-to-zero reciprocal square root: one MUFU, without the denormal rescaling sequence rsqrtf() carries
+SLMGS_DEVICE float fast_rsqrt(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 SLMGS_DEVICE float fast_exp(float x) { return __expf(x); }
 SLMGS_DEVICE float fast_tanh(float x) {
     x = fminf(fmaxf(x, -15.0f), 15.0f);
@@ -77,6 +93,9 @@ SLMGS_DEVICE void fast_sincos(float x, float* s, float* c) { __sincosf(x, s, c);
 #else
 inline float __fdividef(float a, float b) { return a / b; }
 inline float fast_pow(float x, float y) { return powf(x, y); }
+inline float fast_lg2(float x) { return log2f(x); }
+inline float fast_ex2(float x) { return exp2f(x); }
+inline float fast_rsqrt(float x) { return 1.0f / sqrtf(x); }
 inline float fast_exp(float x) { return expf(x); }
 inline float fast_tanh(float x) { return tanhf(x); }
 inline void fast_sincos(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }
@@ -110,6 +129,14 @@ SLMGS_HD float wgs_multiplier(float famp, float t, const WgsParams& q) {
 SLMGS_DEVICE float wgs_multiplier_pow_fast(float famp, float t, const WgsParams& q) {
     float fc = __fdividef(famp * q.inv_fnorm, t);
     fc = fast_pow(fc, -q.p);
+    return (t == 0.0f || !(fc < INFINITY)) ? 1.0f : fc;
+}
+
+// The same from |F|^2: ((|F| s / T)^-p with s = ortho scale / ||F||) = 2^(-p (lg2(|F|^2)/2 + lg2 s - lg2 T)): two
+// logarithms and one exponential instead of a reciprocal square root, a division and a power (lg2s = lg2 s).
+SLMGS_DEVICE float wgs_multiplier_pow_log(float m2, float t, float lg2s, float p) {
+    const float x = fmaf(0.5f, fast_lg2(m2), lg2s) - fast_lg2(t);
+    const float fc = fast_ex2(-p * x);
     return (t == 0.0f || !(fc < INFINITY)) ? 1.0f : fc;
 }
 
@@ -598,6 +625,7 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
         float win = 1.0f;
         if (a.w_in_slot >= 0) win = (float)(1.0 / sqrt(acc[a.w_in_slot]));
         const float fscale = SCALED ? 1.0f : a.scale;
+        const float lg2s = fast_lg2(fscale * a.wgs.inv_fnorm);
         float wsum = 0.0f;
         const float* SLMGS_RESTRICT wp = a.weights + L.ibase;
         const float* SLMGS_RESTRICT tp = a.target + L.tbase;
@@ -638,15 +666,23 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
                 const int off = F::last_index(L.lt + F::TPL * (i / R), i % R) * L.C;
                 const cf z = st.v[i];
                 const float m2 = z.x * z.x + z.y * z.y;
-                const float rinv = m2 > 0.f ? rsqrtf(m2) : 0.f;
+                constexpr bool POWV = !SCALED && (VAR == VAR_POW || VAR == VAR_POW_STORED);
+                // the stored-phase power-law variant needs |F| only inside the logarithm: no reciprocal square root
+                float rinv = 0.f;
+                // (fused path: flush-to-zero MUFU; |F|^2 below 1e-37 is treated like an exact zero, phase 0)
+                const bool nz = SCALED ? (m2 > 0.f) : (m2 > 1.0e-37f);
+                if (!(POWV && VAR == VAR_POW_STORED)) rinv = nz ? (SCALED ? rsqrtf(m2) : fast_rsqrt(m2)) : 0.f;
                 float w = wq[i] * win;
                 const float t = tq[i];
                 if (update) {
-                    const float famp = m2 * rinv * fscale;  // |F| (ortho-scaled)
                     float fc;
-                    if (SCALED) fc = wgs_multiplier(famp, t, a.wgs);
-                    else if (VAR == VAR_POW || VAR == VAR_POW_STORED) fc = wgs_multiplier_pow_fast(famp, t, a.wgs);
-                    else fc = wgs_multiplier_fast(famp, t, a.wgs);
+                    if (POWV) {
+                        fc = wgs_multiplier_pow_log(m2, t, lg2s, a.wgs.p);
+                    } else {
+                        const float famp = m2 * rinv * fscale;  // |F| (ortho-scaled)
+                        if (SCALED) fc = wgs_multiplier(famp, t, a.wgs);
+                        else fc = wgs_multiplier_fast(famp, t, a.wgs);
+                    }
                     w = wgs_apply(w, fc);
                     a.weights[L.ibase + off] = w;
                     wsum += w * w;
@@ -659,7 +695,7 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
                     else fast_sincos(pq[i], &sn, &cs);
                     unit = cmake(cs, sn);
                 } else {
-                    unit = m2 > 0.f ? cmake(z.x * rinv, z.y * rinv) : cmake(1.0f, 0.f);
+                    unit = nz ? cmake(z.x * rinv, z.y * rinv) : cmake(1.0f, 0.f);
                     if (zero_region) unit = cmake(1.0f, 0.f);  // angle taken after farfield[zero] = 0 (:1613-1622)
                     // the fused kernel never stores: the host runs a COL_FWD pass for that iteration instead
                     if (SCALED && a.phase_mode == PHASE_COMPUTE_STORE) a.phase_ff[L.ibase + off] = atan2f(unit.y, unit.x);

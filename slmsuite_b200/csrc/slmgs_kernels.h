@@ -351,8 +351,10 @@ template <int N, int MODE, bool STORE = false, bool SPARSE = false> struct RowKe
                     const float m2 = z.x * z.x + z.y * z.y;
                     const float am = a.amp ? (L.active ? __ldg(a.amp + (long long)id.by * a.amp_bs + (long long)L.sr * a.w + sc) : 0.f)
                                            : a.amp_scalar;
-                    const float r = m2 > 0.f ? rsqrtf(m2) * am : 0.f;
-                    val = m2 > 0.f ? cmake(z.x * r, z.y * r) : cmake(am, 0.f);
+                    // flush-to-zero MUFU rsqrt (no denormal rescaling sequence); |z|^2 below 1e-37 counts as zero
+                    const bool nz = m2 > 1.0e-37f;
+                    const float r = nz ? fast_rsqrt(m2) * am : 0.f;
+                    val = nz ? cmake(z.x * r, z.y * r) : cmake(am, 0.f);
                     if (!inside) val = cmake(0.f, 0.f);
                 }
                 st.v[u * R + m] = val;

@@ -167,10 +167,9 @@ SLMGS_DEVICE float wgs_multiplier_fast(float famp, float t, const WgsParams& q) 
 // weights *= fc; nan_to_num(nan=1e-4)  (:1870-1873; +-inf -> +-FLT_MAX as numpy does)
 SLMGS_HD float wgs_apply(float w, float fc) {
     w = w * fc;
-    if (w != w) return 1.0e-4f;
-    if (w == INFINITY) return FLT_MAX;
-    if (w == -INFINITY) return -FLT_MAX;
-    return w;
+    // branch-free: clamp +-inf to +-FLT_MAX (fminf / fmaxf return the non-NaN operand), then replace NaN
+    const float c = fminf(fmaxf(w, -FLT_MAX), FLT_MAX);
+    return (w != w) ? 1.0e-4f : c;
 }
 
 // ==========================================================================================

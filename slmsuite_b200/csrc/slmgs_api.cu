@@ -119,6 +119,7 @@ struct slmgs_ctx {
     float *phase, *amp, *prop, *target, *weights, *phase_ff, *amp_ff;
     cf *twA_row, *twB_row, *twA_col, *twB_col;
     double* acc;      // [B][ACC_N]
+    float* winf;      // [B] 1/sqrt(sum w^2) of the pending normalisation, written by the row kernels of the fused loop
     double* partial;  // stats partials
     int* spot_x;
     int* spot_y;
@@ -311,7 +312,7 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
     c->fld = nullptr; c->farfield = nullptr; c->stage_c = nullptr; c->stage_f = nullptr;
     c->phase = c->amp = c->prop = c->target = c->weights = c->phase_ff = c->amp_ff = nullptr;
     c->twA_row = c->twB_row = c->twA_col = c->twB_col = nullptr;
-    c->acc = nullptr; c->partial = nullptr;
+    c->acc = nullptr; c->partial = nullptr; c->winf = nullptr;
     c->spot_x = c->spot_y = nullptr; c->spot_amp = nullptr; c->spot_pw = nullptr; c->n_spots = 0;
     c->amp_scalar = (float)(1.0 / sqrt((double)h * (double)w));
     c->amp_per_hologram = 0;
@@ -366,6 +367,7 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
     CR(dev_alloc(c, &c->amp_ff, Bz * P));
     CR(dev_alloc(c, &c->stage_f, Bz * P));
     CR(dev_alloc(c, &c->acc, Bz * ACC_N));
+    CR(dev_alloc(c, &c->winf, Bz));
     CR(dev_alloc(c, &c->partial, Bz * 256 * 8));
     CR(rt_check(c, rt_memset(c->fld, 0, Bz * P * sizeof(cf), c->stream), "memset"));
     CR(rt_check(c, rt_memset(c->phase, 0, Bz * S * sizeof(float), c->stream), "memset"));
@@ -400,7 +402,7 @@ extern "C" int slmgs_destroy(slmgs_ctx* c) {
     void* ptrs[] = {c->fld, c->farfield, c->stage_c, c->stage_f, c->phase, c->amp, c->prop, c->target,
                     c->weights, c->phase_ff, c->amp_ff, c->twA_row, c->twB_row, c->twA_col, c->twB_col, c->acc,
                     c->partial, c->spot_x, c->spot_y, c->spot_amp, c->spot_pw, c->phase_saved, c->mp_sum, c->zero_w,
-                    c->tile_flags, c->tile_list, c->tile_byte, c->tile_count, c->samp_y, c->samp_x, c->scratch};
+                    c->tile_flags, c->tile_list, c->tile_byte, c->tile_count, c->samp_y, c->samp_x, c->scratch, c->winf};
     for (void* p : ptrs)
         if (p) rt_free(p);
 #ifndef SLMGS_EMULATE
@@ -943,6 +945,12 @@ static int run_impl(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
         auto out_slot_after = [&](int pending) { return pending == ACC_W0 ? ACC_W1 : ACC_W0; };
         RowArgs ra = row_args(c);
         if (in_kernel_update(params)) ra.zero_acc = c->acc + out_slot_after(c->w_pending);
+        // the row kernel in front of a column kernel turns the pending sum(w^2) into the float factor that kernel uses
+        auto set_win = [&](RowArgs& r) {
+            r.win_src = c->w_pending >= 0 ? c->acc + c->w_pending : nullptr;
+            r.win_dst = c->w_pending >= 0 ? c->winf : nullptr;
+        };
+        set_win(ra);
         if ((e = run_row(c, ROW_FIRST, ra))) return e;
         for (int i = 0; i < n_iter; ++i) {
             const slmgs_params* p = params + i;
@@ -967,12 +975,14 @@ static int run_impl(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
             }
             ca.wgs_update = in_kernel ? 1 : 0;
             ca.w_in_slot = c->w_pending;
+            ca.win_f = c->winf;
             if (ca.wgs_update) ca.w_out_slot = out_slot_after(c->w_pending);
             if ((e = run_col(c, COL_FUSED, ca))) return e;
             if (ca.wgs_update) c->w_pending = ca.w_out_slot;
             ra.store_phase = (i == n_iter - 1);
             ra.zero_acc = nullptr;
             if (i + 1 < n_iter && in_kernel_update(params + i + 1)) ra.zero_acc = c->acc + out_slot_after(c->w_pending);
+            set_win(ra);
             if ((e = run_row(c, ROW_FUSED, ra))) return e;
         }
     }

@@ -195,6 +195,8 @@ struct RowArgs {
     int mp_first;        // first child of the sum: overwrite instead of add
     double* zero_acc;    // accumulator slot to clear for the next column kernel ([B] slots, stride zero_bs), or nullptr
     int zero_bs;
+    const double* win_src;  // accumulator slot holding sum(w^2) of a pending weight normalisation ([B], stride zero_bs): this
+    float* win_dst;         // kernel converts it to 1/sqrt(.) in float32 for the column kernel that follows ([B]), or nullptr
     int pdl;             // launch with programmatic dependent launch
     int pf_dist;         // L2 prefetch distance in tiles (blocks resident on the GPU), 0 = off
     long long colflag_bs;          // per-hologram stride of colflag
@@ -365,6 +367,8 @@ template <int N, int MODE, bool STORE = false, bool SPARSE = false> struct RowKe
         const Loc L = locate(a, smem, id);
         if constexpr (P == 0) {
             if (a.zero_acc && id.bx == 0 && id.tid == 0) a.zero_acc[(long long)id.by * a.zero_bs] = 0.0;
+            if (a.win_dst && id.bx == 0 && id.tid == 0)
+                a.win_dst[id.by] = (float)(1.0 / sqrt(a.win_src[(long long)id.by * a.zero_bs]));
             if (MODE != ROW_FIRST && a.pf_dist > 0) {
                 // pull the rows of the tile this SM will run next into L2 while this tile computes
                 const int lines = id.nthreads / F::TPL;
@@ -428,6 +432,7 @@ struct ColArgs {
     double* acc;          // [B][acc_bs] accumulators
     int acc_bs;
     int w_in_slot;        // accumulator slot holding sum(w^2) of a pending normalisation, or -1
+    const float* win_f;   // [B] 1/sqrt of that slot, prepared by the preceding row kernel (fused loop), or nullptr
     int w_out_slot;       // accumulator slot receiving sum(w_new^2), or -1
     int H, W, h, i0;
     float scale;          // 1/sqrt(H W): ortho normalisation of the forward transform
@@ -624,7 +629,7 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
         const bool need_t = update || mraf;
         double* acc = a.acc + (long long)id.by * a.acc_bs;
         float win = 1.0f;
-        if (a.w_in_slot >= 0) win = (float)(1.0 / sqrt(acc[a.w_in_slot]));
+        if (a.w_in_slot >= 0) win = (!SCALED && a.win_f) ? __ldg(a.win_f + id.by) : (float)(1.0 / sqrt(acc[a.w_in_slot]));
         const float fscale = SCALED ? 1.0f : a.scale;
         const float lg2s = fast_lg2(fscale * a.wgs.inv_fnorm);
         float wsum = 0.0f;

@@ -194,13 +194,14 @@ SLMGS_API int slmgs_time_kernel(slmgs_ctx*, int which, int n, float* ms_out);
  * CompressedSpotHologram, slmsuite/holography/algorithms/_spots.py:178-1019: instead of a DFT grid every spot n owns a
  * phase kernel phi_n(pix) = sum_d spot_zernike[d, n] Z_d(x_pix, y_pix) (_spots.py:595-636) and the maps of the GS loop
  * are direct sums over pixels / spots (the reference's NumPy matmul pair :767-824 / :887-915 and its CUDA pair
- * toolbox/cuda.cu:95-288).  The host expands the Zernike basis into monomials: mono[m][pix] = x^px y^py (float64,
- * aperture-scaled grid) and cw[m][n] = sum_d c[m, d] spot_zernike[d, n] (float64, radians), at most 10 monomials.
+ * toolbox/cuda.cu:95-288).  The host evaluates the M <= 10 basis functions once: mono[m][pix] = Z_m(x_pix, y_pix)
+ * (float64, aperture-scaled grid; any functions whose weighted sum is the phase) and cw[m][n] = spot_zernike[m, n]
+ * (float64, radians).
  * Targets / weights / far field are N-vectors; the target may hold NaN (MRAF noise point) and 0 (null point).
  * slmgs_params as for slmgs_run (feedback is always the computed spot amplitude, _spots.py:950-989). */
 typedef struct slmgs_comp slmgs_comp;
 SLMGS_API const char* slmgs_comp_last_error(const slmgs_comp*);
-SLMGS_API int slmgs_comp_create(slmgs_comp** out, int device, int h, int w, int n_spots, int n_monomials);
+SLMGS_API int slmgs_comp_create(slmgs_comp** out, int device, int h, int w, int n_spots, int n_basis);
 SLMGS_API int slmgs_comp_destroy(slmgs_comp*);
 SLMGS_API int slmgs_comp_sync(slmgs_comp*);
 SLMGS_API long long slmgs_comp_launch_count(const slmgs_comp*);

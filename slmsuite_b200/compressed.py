@@ -155,21 +155,27 @@ class CompressedSpotHologram(Hologram):
         self.cameraslm = cameraslm
         self.propagation_kernel = None
 
-        # host setup of the phase kernels: monomials of the basis on the aperture-scaled grid (_spots.py:609-614
-        # stores the scaled grid as complex64, i.e. rounded to float32) and per-spot monomial weights
+        # host setup of the phase kernels: the basis functions Z_d on the aperture-scaled grid (_spots.py:609-614 stores
+        # the scaled grid as complex64, i.e. rounded to float32), evaluated once in float64 from their monomial
+        # expansion; the device then needs D double FMAs per (pixel, spot) pair
         px, py, c = monomial_table(self.zernike_basis)
         self._px, self._py, self._c = px, py, c
         x = np.array(np.asarray(x_grid) * zernike_scaling, dtype=np.float32).astype(np.float64).ravel()
         y = np.array(np.asarray(y_grid) * zernike_scaling, dtype=np.float32).astype(np.float64).ravel()
-        mono = np.empty((len(px), x.size), dtype=np.float64)
+        if D > 10:
+            raise ValueError("a Zernike basis of more than 10 terms is not supported on the B200 path")
+        mono = np.zeros((D, x.size), dtype=np.float64)
         for m in range(len(px)):
-            mono[m] = x ** int(px[m]) * y ** int(py[m])
+            term = x ** int(px[m]) * y ** int(py[m])
+            for d in range(D):
+                if c[m, d] != 0:
+                    mono[d] += c[m, d] * term
 
         self._device = int(device)
         self._ctx = C.c_void_p()
         self._lib = _lib.lib()
         status = self._lib.slmgs_comp_create(C.byref(self._ctx), self._device, self.slm_shape[0], self.slm_shape[1],
-                                             N, len(px))
+                                             N, D)
         if status != _lib.OK:
             msg = self._lib.slmgs_comp_last_error(None)
             raise (ValueError if status == _lib.ERR_INVALID else RuntimeError)(msg.decode() if msg else "slmgs error")
@@ -223,7 +229,7 @@ class CompressedSpotHologram(Hologram):
         return self.spot_amp.size
 
     def _upload_basis(self):
-        cw = np.ascontiguousarray(self._c @ self.spot_zernike, dtype=np.float64)  # (M, N), toolbox/phase.py:905
+        cw = np.ascontiguousarray(self.spot_zernike, dtype=np.float64)  # (D, N): weights of the basis functions
         self._check(self._lib.slmgs_comp_set_basis(self._ctx, _lib.dptr(self._mono), _lib.dptr(cw)))
         self._spot_zernike_cached = self.spot_zernike.copy()
 

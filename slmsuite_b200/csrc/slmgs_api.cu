@@ -1557,12 +1557,12 @@ extern "C" int slmgs_comp_create(slmgs_comp** out, int device, int h, int w, int
     *out = nullptr;
     if (h < 1 || w < 1 || n_spots < 1) return cfail(nullptr, SLMGS_ERR_INVALID, "slm_shape and the number of spots must be positive");
     if (n_monomials < 1 || n_monomials > 10)
-        return cfail(nullptr, SLMGS_ERR_INVALID, "the Zernike basis must expand into 1..10 monomials (up to third order)");
+        return cfail(nullptr, SLMGS_ERR_INVALID, "the basis must have 1..10 functions");
     int e = rt_set_device(device);
     if (e) return cfail(nullptr, SLMGS_ERR_CUDA, std::string("cudaSetDevice: ") + rt_errstr(e));
     slmgs_comp* c = new slmgs_comp();
     c->device = device; c->h = h; c->w = w; c->N = n_spots; c->M = n_monomials;
-    c->MT = n_monomials <= 2 ? 2 : n_monomials <= 6 ? 6 : 10;
+    c->MT = n_monomials <= 2 ? 2 : n_monomials <= 3 ? 3 : n_monomials <= 6 ? 6 : 10;
     c->S = (long long)h * w;
     c->launches = 0;
     c->sms = rt_sm_count();
@@ -1610,7 +1610,7 @@ extern "C" int slmgs_comp_sync(slmgs_comp* c) {
 }
 extern "C" long long slmgs_comp_launch_count(const slmgs_comp* c) { return c ? c->launches : 0; }
 
-// mono: [M][h*w] float64 monomial values; cw: [M][N] float64 per-spot monomial weights in RADIANS
+// mono: [M][h*w] float64 basis-function values; cw: [M][N] float64 per-spot weights of the basis functions in RADIANS
 extern "C" int slmgs_comp_set_basis(slmgs_comp* c, const double* mono, const double* cw) {
     CHECK_COMP(c);
     if (!mono || !cw) return cfail(c, SLMGS_ERR_INVALID, "mono / cw is NULL");
@@ -1683,6 +1683,7 @@ static CompArgs comp_args(slmgs_comp* c) {
 template <template <int> class K> static int comp_launch_mt(slmgs_comp* c, int gx, int gy, const CompArgs& a) {
     c->launches++;
     if (c->MT == 2) return launch_kernel<K<2>>(gx, gy, 256, 0, c->stream, a);
+    if (c->MT == 3) return launch_kernel<K<3>>(gx, gy, 256, 0, c->stream, a);
     if (c->MT == 6) return launch_kernel<K<6>>(gx, gy, 256, 0, c->stream, a);
     return launch_kernel<K<10>>(gx, gy, 256, 0, c->stream, a);
 }

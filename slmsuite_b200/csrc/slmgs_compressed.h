@@ -7,10 +7,11 @@
 //     nearfield[pix] = sum_n farfield[n] exp(+i phi_n(pix)) / sqrt(S)                                      (:887-915)
 // (the reference's own CUDA pair for this is toolbox/cuda.cu:95-288: one thread per pixel, per-spot 1024-thread
 // shared-memory tree reduction).  Here:
-//   * the host expands the basis into monomials once (mono[m][pix], float64) and folds the spot coefficients into
-//     per-spot monomial weights cw[m][n] = sum_d c[m, d] a[d, n] / (2 pi), so phi/(2 pi) = sum_m cw[m][n] mono[m][pix]
-//     is M double FMAs per (pixel, spot); the turn count is reduced in double (t - rint(t)) before sincospif, so the
-//     phase is exact to float32 rounding however many radians it spans (the reference accumulates it in float32);
+//   * the host evaluates the basis functions once (mono[m][pix] = Z_m(x_pix, y_pix), float64, from their monomial
+//     expansion) and passes the spot coefficients in turns, cw[m][n] = a[m, n] / (2 pi), so phi/(2 pi) = sum_m cw[m][n]
+//     mono[m][pix] is M = D double FMAs per (pixel, spot); the turn count is reduced in double before the MUFU sine /
+//     cosine, so the phase is exact to float32 rounding however many radians it spans (the reference accumulates it
+//     in float32);
 //   * near -> far: a thread keeps PPT pixels (monomials + near field) in registers and 16 spot accumulators, loads the
 //     spot weights once per PPT pixels (L1 broadcast), and a block contributes one warp-reduced atomicAdd(double) per
 //     warp and spot; far -> near: a thread keeps PPT pixels and loops over all spots; the phase-only projection
@@ -28,9 +29,9 @@ enum { COMP_SPOTS = 16, COMP_PPT = 4 };
 struct CompArgs {
     long long S;          // SLM pixels
     int N;                // spots
-    int M;                // monomials in use (<= MT of the instantiation)
-    const double* mono;   // [MT][S]   monomial values x^px y^py per pixel (rows >= M are zero)
-    const double* cw;     // [MT][N]   per-spot monomial weights in turns (rows >= M are zero)
+    int M;                // basis functions in use (<= MT of the instantiation)
+    const double* mono;   // [MT][S]   basis-function values per pixel (rows >= M are zero)
+    const double* cw;     // [MT][N]   per-spot weights of the basis functions in turns (rows >= M are zero)
     const float* phase;   // [S]
     const float* amp;     // [S] or nullptr
     float amp_scalar;

@@ -160,7 +160,7 @@ def test_errors(backend):
     with pytest.raises(ValueError):
         CompressedSpotHologram(g["spot_vectors"], spot_amp=np.ones(3), slm_grid=grid, zernike_scaling=1.0)
     with pytest.raises(ValueError):
-        CompressedSpotHologram(np.zeros((14, 4)), basis=list(range(1, 15)), slm_grid=grid, zernike_scaling=1.0)  # > 10 monomials
+        CompressedSpotHologram(np.zeros((14, 4)), basis=list(range(1, 15)), slm_grid=grid, zernike_scaling=1.0)  # > 10 basis terms
     h = build(CompressedSpotHologram, g, "compressed_2d_leonardo")
     with pytest.raises(NameError):
         h.get_padded_shape((64, 64))

@@ -816,7 +816,7 @@ static int prepare_sparse(slmgs_ctx* c, const slmgs_params* params, int n_iter) 
     const int C = c->col_threads / c->icol.tpl;
     const int ntiles = c->W / C;
     const size_t B = (size_t)c->B;
-    if (ntiles < 4) return 0;
+    if (ntiles < 4 || C * 16 > c->W) return 0;  // (the row kernel's flag layout needs whole tiles per W/16 columns)
     int e;
     if (!c->tile_flags) {
         if ((e = dev_alloc(c, &c->tile_flags, B * ntiles))) return e;
@@ -863,9 +863,11 @@ static int prepare_sparse(slmgs_ctx* c, const slmgs_params* params, int n_iter) 
         int most = 0;
         for (size_t b = 0; b < B; ++b) {
             int n = 0;
+            const int ts = ntiles / 16;  // tiles per W/16 columns
             for (int t = 0; t < ntiles; ++t) {
                 const bool a = (c->tile_flags_h[b * ntiles + t] & (mraf ? 3 : 1)) || win[t];
-                on[b * ntiles + t] = a ? 1 : 0;
+                // row-kernel order (RowArgs::colflag): tile q + ts * m at byte 16 q + m
+                on[b * ntiles + (size_t)(t % ts) * 16 + t / ts] = a ? 1 : 0;
                 if (a) list[b * ntiles + n++] = t;
             }
             count[b] = n;

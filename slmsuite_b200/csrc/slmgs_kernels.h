@@ -200,6 +200,9 @@ struct RowArgs {
     int pdl;             // launch with programmatic dependent launch
     int pf_dist;         // L2 prefetch distance in tiles (blocks resident on the GPU), 0 = off
     long long colflag_bs;          // per-hologram stride of colflag
+    // The flags are stored in the order the row kernel reads them: a thread's last-stage butterfly b touches columns
+    // b + (W/16) m, m = 0..15, i.e. column tiles q + TS m with q = b / C and TS = (W/16) / C; tile q + TS m sits at byte
+    // 16 q + m, so the thread fetches its sixteen flags with ONE 16-byte load.
     const unsigned char* colflag;  // sparse far field: one byte per column tile of the column kernel (1 = the tile is
                                    // processed by the column kernel); columns of other tiles are identically zero after
                                    // the far-field constraint, so they are neither stored nor loaded.  nullptr = dense
@@ -239,7 +242,6 @@ template <int N, int MODE, bool STORE = false, bool SPARSE = false> struct RowKe
         long long cbase;  // this hologram's offset into colflag
         bool active;
     };
-    static SLMGS_DEVICE long long id_by_off(const Args&, const Loc& L) { return L.cbase; }
     static SLMGS_DEVICE Loc locate(const Args& a, cf* smem, const ThreadId& id) {
         Loc L;
         const int line = id.tid / F::TPL;
@@ -263,16 +265,36 @@ template <int N, int MODE, bool STORE = false, bool SPARSE = false> struct RowKe
         return a.amp ? __ldg(a.amp + (long long)id.by * a.amp_bs + (long long)L.sr * a.w + sc) : a.amp_scalar;
     }
 
+    // the sixteen column-tile flags of last-stage butterfly u of this thread (see RowArgs::colflag)
+    struct Flags16 {
+        unsigned w[4];
+    };
+    static SLMGS_DEVICE Flags16 load_flags(const Args& a, const Loc& L, int u) {
+        Flags16 f;
+        const int q = (L.lt + F::TPL * u) >> a.ctile_shift;
+        const unsigned char* p = a.colflag + L.cbase + (long long)q * 16;
+#if defined(__CUDACC__) && !defined(SLMGS_EMULATE)
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+        f.w[0] = v.x; f.w[1] = v.y; f.w[2] = v.z; f.w[3] = v.w;
+#else
+        memcpy(f.w, p, 16);
+#endif
+        return f;
+    }
+    static SLMGS_DEVICE bool flag_byte(const Flags16& f, int m) { return ((f.w[m >> 2] >> ((m & 3) * 8)) & 0xffu) != 0; }
+
     // v <- spectrum of this row (inverse input), natural last-stage order
     static SLMGS_DEVICE void load_spectrum(State& st, const Args& a, const Loc& L) {
         constexpr int R = F::last_radix();
         SLMGS_UNROLL
         for (int u = 0; u < E / R; ++u) {
+            Flags16 fl;
+            if (SPARSE) fl = load_flags(a, L, u);
             SLMGS_UNROLL
             for (int m = 0; m < R; ++m) {
                 const int k = F::last_index(L.lt + F::TPL * u, m);
                 bool on = L.active;
-                if (SPARSE) on = on && __ldg(a.colflag + id_by_off(a, L) + (k >> a.ctile_shift)) != 0;
+                if (SPARSE) on = on && flag_byte(fl, m);
                 st.v[u * R + m] = on ? ld_stream(a.fld + L.fbase + k) : cmake(0.f, 0.f);
             }
         }
@@ -282,10 +304,12 @@ template <int N, int MODE, bool STORE = false, bool SPARSE = false> struct RowKe
         if (!L.active) return;
         SLMGS_UNROLL
         for (int u = 0; u < E / R; ++u) {
+            Flags16 fl;
+            if (SPARSE) fl = load_flags(a, L, u);
             SLMGS_UNROLL
             for (int m = 0; m < R; ++m) {
                 const int k = F::last_index(L.lt + F::TPL * u, m);
-                if (SPARSE && __ldg(a.colflag + id_by_off(a, L) + (k >> a.ctile_shift)) == 0) continue;
+                if (SPARSE && !flag_byte(fl, m)) continue;
                 a.fld[L.fbase + k] = st.v[u * R + m];
             }
         }

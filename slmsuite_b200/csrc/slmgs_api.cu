@@ -695,6 +695,9 @@ static ColArgs col_args(slmgs_ctx* c) {
     a.acc_bs = ACC_N;
     a.w_in_slot = -1;
     a.w_out_slot = -1;
+    a.ratio_slot = -1;
+    a.ratio_extra = 0.0;
+    a.inv_npix = 1.0 / ((double)c->H * (double)c->W);
     a.H = c->H; a.W = c->W; a.h = c->h; a.i0 = c->i0;
     a.scale = (float)(1.0 / sqrt((double)c->H * (double)c->W));
     a.wgs.method = METHOD_GS;
@@ -801,12 +804,15 @@ static int update_weights_spot_impl(slmgs_ctx* c, const slmgs_params* p, int wid
 static int prepare_sparse(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
     c->sparse_now = false;
     if (!c->sparse_mode || n_iter < 1) return 0;
-    int mraf = 0, spot_width = 0;
+    int mraf = 0, spot_width = 0, nogrette = 0;
     for (int i = 0; i < n_iter; ++i) {
         const slmgs_params* p = params + i;
         if (p->mraf && p->zero_weights) return 0;   // farfield[zero] = zero_weights: dense by construction
-        if (p->update_weights && p->feedback == 0 && (p->mraf || p->method == SLMGS_WGS_NOGRETTE))
-            return 0;                               // pixel updates with a global sum over |farfield| need every tile
+        if (p->update_weights && p->feedback == 0 && p->mraf)
+            return 0;                               // MRAF + pixel feedback: a global sum over |farfield| needs every tile
+        // WGS-Nogrette's mean runs over the whole far field, but the ratio is exactly 1 wherever the target is zero:
+        // tiles with a non-zero target stay active and the others are counted analytically
+        if (p->update_weights && p->feedback == 0 && p->method == SLMGS_WGS_NOGRETTE) nogrette = 1;
         if (p->mraf) mraf = 1;
         if (p->update_weights && p->feedback == 1) {
             if (spot_width && spot_width != p->spot_width) return 0;
@@ -842,7 +848,8 @@ static int prepare_sparse(slmgs_ctx* c, const slmgs_params* params, int n_iter) 
         c->tiles_dirty = false;
         c->tile_key = -1;
     }
-    const int key = mraf | (spot_width << 1);
+    const int key = mraf | (nogrette << 1) | (spot_width << 2);
+    const int mask = 1 | (mraf ? 2 : 0) | (nogrette ? 4 : 0);
     if (key != c->tile_key) {
         // tiles under the analysis.take windows (SpotGatherKernel): x_n + floor(k - (w-1)/2), negative indices wrap;
         // the spot list is shared by the batch
@@ -865,7 +872,7 @@ static int prepare_sparse(slmgs_ctx* c, const slmgs_params* params, int n_iter) 
             int n = 0;
             const int ts = ntiles / 16;  // tiles per W/16 columns
             for (int t = 0; t < ntiles; ++t) {
-                const bool a = (c->tile_flags_h[b * ntiles + t] & (mraf ? 3 : 1)) || win[t];
+                const bool a = (c->tile_flags_h[b * ntiles + t] & mask) || win[t];
                 // row-kernel order (RowArgs::colflag): tile q + ts * m at byte 16 q + m
                 on[b * ntiles + (size_t)(t % ts) * 16 + t / ts] = a ? 1 : 0;
                 if (a) list[b * ntiles + n++] = t;
@@ -889,7 +896,7 @@ static int prepare_sparse(slmgs_ctx* c, const slmgs_params* params, int n_iter) 
     if (c->sparse_now) {
         for (size_t b = 0; b < B && c->sparse_now; ++b) {
             bool any = false;
-            for (int t = 0; t < ntiles && !any; ++t) any = (c->tile_flags_h[b * ntiles + t] & (mraf ? 3 : 1)) != 0;
+            for (int t = 0; t < ntiles && !any; ++t) any = (c->tile_flags_h[b * ntiles + t] & mask) != 0;
             if (!any && spot_width == 0) c->sparse_now = false;
         }
     }
@@ -940,8 +947,11 @@ static int run_impl(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
         auto in_kernel_update = [&](const slmgs_params* p) {
             return p->update_weights && p->feedback == 0 && !p->mraf &&
                    (p->method == SLMGS_WGS_LEONARDO || p->method == SLMGS_WGS_KIM || p->method == SLMGS_WGS_WU ||
-                    p->method == SLMGS_WGS_TANH);
+                    p->method == SLMGS_WGS_TANH || p->method == SLMGS_WGS_NOGRETTE);
         };
+        // WGS-Nogrette needs mean(ratio) over the whole far field before any weight changes (:1851-1852): a forward
+        // column pre-pass accumulates the sum of the ratio (no stores), the fused kernel then updates with that mean
+        auto needs_ratio = [&](const slmgs_params* p) { return in_kernel_update(p) && p->method == SLMGS_WGS_NOGRETTE; };
         // the accumulator slot that receives sum(w^2) alternates; the row kernel that precedes a column kernel
         // clears that kernel's slot (no memset node between the kernels)
         auto out_slot_after = [&](int pending) { return pending == ACC_W0 ? ACC_W1 : ACC_W0; };
@@ -953,6 +963,7 @@ static int run_impl(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
             r.win_dst = c->w_pending >= 0 ? c->winf : nullptr;
         };
         set_win(ra);
+        if (needs_ratio(params)) ra.zero_acc2 = c->acc + ACC_MEAN;
         if ((e = run_row(c, ROW_FIRST, ra))) return e;
         for (int i = 0; i < n_iter; ++i) {
             const slmgs_params* p = params + i;
@@ -961,12 +972,20 @@ static int run_impl(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
             const bool in_kernel = in_kernel_update(p);
             const bool need_amp = p->update_weights && !in_kernel;
             const bool need_phase = ca.phase_mode == PHASE_COMPUTE_STORE;
-            if (need_amp || need_phase) {
+            const bool need_ratio = needs_ratio(p);
+            if (need_ratio) ca.ratio_slot = ACC_MEAN;  // cleared by the row kernel in front of this iteration
+            if (need_amp || need_phase || need_ratio) {
                 // one forward column pass for |farfield| (global-dependency updates: Nogrette mean, per-spot
                 // windows, MRAF + WGS) and/or angle(farfield) (the WGS-Kim iteration that fixes the phase)
                 ColArgs fa = col_args(c);
                 fa.store_ampff = need_amp;
                 fa.store_phaseff = need_phase;
+                if (need_ratio) {
+                    fa.ratio_slot = ACC_MEAN;
+                    fa.wgs.method = p->method;
+                    fa.wgs.p = p->feedback_exponent;
+                    fa.wgs.f = p->feedback_factor;
+                }
                 if ((e = run_col(c, COL_FWD, fa))) return e;
                 if (need_phase) ca.phase_mode = PHASE_STORED;
             }
@@ -985,6 +1004,7 @@ static int run_impl(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
             ra.zero_acc = nullptr;
             if (i + 1 < n_iter && in_kernel_update(params + i + 1)) ra.zero_acc = c->acc + out_slot_after(c->w_pending);
             set_win(ra);
+            ra.zero_acc2 = (i + 1 < n_iter && needs_ratio(params + i + 1)) ? c->acc + ACC_MEAN : nullptr;
             if ((e = run_row(c, ROW_FUSED, ra))) return e;
         }
     }

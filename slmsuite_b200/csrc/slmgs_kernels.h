@@ -194,6 +194,7 @@ struct RowArgs {
     float mp_weight;
     int mp_first;        // first child of the sum: overwrite instead of add
     double* zero_acc;    // accumulator slot to clear for the next column kernel ([B] slots, stride zero_bs), or nullptr
+    double* zero_acc2;   // a second one (WGS-Nogrette's ratio sum), or nullptr
     int zero_bs;
     const double* win_src;  // accumulator slot holding sum(w^2) of a pending weight normalisation ([B], stride zero_bs): this
     float* win_dst;         // kernel converts it to 1/sqrt(.) in float32 for the column kernel that follows ([B]), or nullptr
@@ -391,6 +392,7 @@ template <int N, int MODE, bool STORE = false, bool SPARSE = false> struct RowKe
         const Loc L = locate(a, smem, id);
         if constexpr (P == 0) {
             if (a.zero_acc && id.bx == 0 && id.tid == 0) a.zero_acc[(long long)id.by * a.zero_bs] = 0.0;
+            if (a.zero_acc2 && id.bx == 0 && id.tid == 0) a.zero_acc2[(long long)id.by * a.zero_bs] = 0.0;
             if (a.win_dst && id.bx == 0 && id.tid == 0)
                 a.win_dst[id.by] = (float)(1.0 / sqrt(a.win_src[(long long)id.by * a.zero_bs]));
             if (MODE != ROW_FIRST && a.pf_dist > 0) {
@@ -469,6 +471,10 @@ struct ColArgs {
     cf* zero_w;           // MRAF zero-region accumulator image ([B][H][W], tile-major), or nullptr (_hologram.py:1613-1616)
     float zero_factor;
     int store_ampff, store_phaseff, store_farfield;  // COL_FWD outputs
+    int ratio_slot;       // COL_FWD: accumulate sum(wgs_ratio(|F| / ||F||, target)) here (WGS-Nogrette's mean, :1851-1852), or -1
+                          // COL_FUSED: Nogrette mean = (acc[ratio_slot] + ratio_extra) * inv_npix, or -1
+    double ratio_extra;   // added to the sum (pixels that were not visited and whose ratio is known to be 1), normally 0
+    double inv_npix;      // 1 / (H W)
     int pdl;              // launch with programmatic dependent launch
     int pf_dist;          // L2 prefetch distance in tiles (blocks resident on the GPU), 0 = off
     const int* tiles;     // sparse far field: blockIdx.x -> column tile (only tiles whose constrained far field can be
@@ -567,7 +573,7 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
         }
     }
     // COL_FWD epilogue: _hologram.py:951-953 (amp_ff), :934-949 (phase_ff), farfield (ortho-scaled)
-    static SLMGS_DEVICE void store_farfield(State& st, const Args& a, const Loc& L) {
+    static SLMGS_DEVICE void store_farfield(State& st, const Args& a, const ThreadId& id, const Loc& L) {
         constexpr int R = F::last_radix();
         SLMGS_UNROLL
         for (int u = 0; u < E / R; ++u) {
@@ -579,6 +585,20 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
                 if (a.store_ampff) a.amp_ff[L.ibase + off] = sqrtf(z.x * z.x + z.y * z.y);
                 if (a.store_phaseff) a.phase_ff[L.ibase + off] = atan2f(z.y, z.x);
             }
+        }
+        if (a.ratio_slot >= 0) {  // every thread of the block gets here (accum_add needs full warps)
+            WgsParams q = a.wgs;
+            double rs = 0.0;
+            SLMGS_UNROLL
+            for (int u = 0; u < E / R; ++u) {
+                SLMGS_UNROLL
+                for (int m = 0; m < R; ++m) {
+                    const long long off = (long long)F::last_index(L.lt + F::TPL * u, m) * L.C;
+                    const cf z = cscale(st.v[u * R + m], a.scale);
+                    rs += (double)wgs_ratio(sqrtf(z.x * z.x + z.y * z.y), ld_stream(a.target + L.tbase + off), q);
+                }
+            }
+            accum_add(a.acc + (long long)id.by * a.acc_bs + a.ratio_slot, rs);
         }
     }
 
@@ -656,6 +676,12 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
         if (a.w_in_slot >= 0) win = (!SCALED && a.win_f) ? __ldg(a.win_f + id.by) : (float)(1.0 / sqrt(acc[a.w_in_slot]));
         const float fscale = SCALED ? 1.0f : a.scale;
         const float lg2s = fast_lg2(fscale * a.wgs.inv_fnorm);
+        WgsParams wq_params = a.wgs;
+        if (GEN && !SCALED && a.ratio_slot >= 0) {  // WGS-Nogrette in the fused loop: mean of the ratio from the pre-pass
+            // sparse far field: the tiles that were not launched hold target == 0 only, where the ratio is exactly 1 (:1841)
+            const double skipped = a.tiles ? (double)a.H * (double)(a.W - __ldg(a.tile_count + id.by) * L.C) : 0.0;
+            wq_params.neg_inv_mean = -(1.0f / (float)((acc[a.ratio_slot] + a.ratio_extra + skipped) * a.inv_npix));
+        }
         float wsum = 0.0f;
         const float* SLMGS_RESTRICT wp = a.weights + L.ibase;
         const float* SLMGS_RESTRICT tp = a.target + L.tbase;
@@ -711,7 +737,7 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
                     } else {
                         const float famp = m2 * rinv * fscale;  // |F| (ortho-scaled)
                         if (SCALED) fc = wgs_multiplier(famp, t, a.wgs);
-                        else fc = wgs_multiplier_fast(famp, t, a.wgs);
+                        else fc = wgs_multiplier_fast(famp, t, wq_params);
                     }
                     w = wgs_apply(w, fc);
                     a.weights[L.ibase + off] = w;
@@ -758,7 +784,7 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
         if constexpr (MODE == COL_FWD) {
             if constexpr (P == 0) load_rows(st, a, L);
             F::template fwd_stage<P>(st.v, L.lt, a.twA, a.twB, L.s, L.C);
-            if constexpr (P == NS - 1) store_farfield(st, a, L);
+            if constexpr (P == NS - 1) store_farfield(st, a, id, L);
         } else if constexpr (MODE == COL_INV) {
             if constexpr (P == 0) {
                 load_farfield(st, a, L);

@@ -311,7 +311,8 @@ struct SpotUpdateKernel {
 // exp(i phase_ff) (_hologram.py:1601-1605) is identically zero wherever weights == 0 -- and a weight that
 // is zero stays zero under every WGS update (:1870, W *= fc with fc finite) -- except in an MRAF noise
 // region (target is NaN, :1643-1653), which passes the field through.  One block per (tile, hologram):
-//   flags[tile] |= 1 if any weight of the tile is non-zero (or NaN), |= 2 if any target value is NaN.
+//   flags[tile] |= 1 if any weight of the tile is non-zero (or NaN), |= 2 if any target value is NaN,
+//                |= 4 if any target value is non-zero (WGS-Nogrette's mean runs over the ratio |F| / T, which is 1 where T == 0).
 // The images are tile-major, so a tile is one contiguous block of H*C floats.
 // ------------------------------------------------------------------------------------------
 struct TileArgs {
@@ -345,6 +346,7 @@ struct TileFlagKernel {
             const float wv = ld_stream(w + i), tv = ld_stream(t + i);
             if (!(wv == 0.0f)) f |= 1;
             if (tv != tv) f |= 2;
+            else if (tv != 0.0f) f |= 4;
         }
         if (f) atomic_or_int(a.flags + (long long)id.by * a.flags_bs + id.bx, f);
     }

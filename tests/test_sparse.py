@@ -199,3 +199,51 @@ def test_batch_has_per_hologram_occupancy(backend):
     _same(a.phase, b.phase, 2e-5)
     _same(a.amp_ff, b.amp_ff, 2e-6)
     _same(a.weights, b.weights, 2e-6)
+
+
+def test_nogrette_sparse_equals_dense(backend):
+    """WGS-Nogrette's mean(ratio) runs over the whole far field (_hologram.py:1851-1852); the ratio is exactly 1 where
+    the target is zero, so tiles without target are skipped and counted.  Includes user weights on a column that has
+    no target (inactive for the constraint's purposes only if its weights were zero) and a batch."""
+    from slmsuite_b200 import HologramBatch
+
+    rng = np.random.default_rng(9)
+    shape = (128, 256)
+    target = _spot_target(shape, [3, 4, 77, 130, 255], 3, rng)
+    phase = rng.uniform(-np.pi, np.pi, shape).astype(np.float32)
+    kw = dict(target=target, phase=phase)
+    opt = dict(method="WGS-Nogrette", maxiter=6)
+    a = _run(kw, opt, True)
+    b = _run(kw, opt, False)
+    assert a.sparse_info()[0] and not b.sparse_info()[0]
+    _same(a.phase, b.phase, 2e-5)
+    _same(a.amp_ff, b.amp_ff, 2e-6)
+    _same(a.weights, b.weights, 2e-6)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = gs_oracle.OracleHologram(target, phase=phase)
+        ref.optimize(verbose=False, **opt)
+    assert np.linalg.norm(a.amp_ff - ref.amp_ff) / np.linalg.norm(ref.amp_ff) <= 1e-5
+    assert np.linalg.norm(a.weights - ref.weights) / np.linalg.norm(ref.weights) <= 1e-5
+    # weights on a target-free column
+    w = target.copy()
+    w[10, 200] = 0.3
+    a = _run(kw, opt, True, weights=w)
+    b = _run(kw, opt, False, weights=w)
+    assert a.sparse_info()[0]
+    _same(a.weights, b.weights, 2e-6)
+    _same(a.amp_ff, b.amp_ff, 2e-6)
+    # batch: every hologram counts its own skipped tiles
+    targets = np.stack([_spot_target(shape, cols, 2, rng) for cols in ([5, 6, 7, 100], [100], [250, 30])])
+    phases = rng.uniform(-np.pi, np.pi, (3,) + shape).astype(np.float32)
+    res = []
+    for sparse in (True, False):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            hb = HologramBatch(targets, phase=phases)
+            hb.set_sparse(sparse)
+            hb.optimize("WGS-Nogrette", maxiter=4, verbose=False)
+        res.append(hb)
+    assert res[0].sparse_info()[0]
+    _same(res[0].weights, res[1].weights, 2e-6)
+    _same(res[0].phase, res[1].phase, 2e-5)

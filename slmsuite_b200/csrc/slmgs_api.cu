@@ -696,6 +696,7 @@ static ColArgs col_args(slmgs_ctx* c) {
     a.w_in_slot = -1;
     a.w_out_slot = -1;
     a.ratio_slot = -1;
+    a.wsq_slot = -1;
     a.ratio_extra = 0.0;
     a.inv_npix = 1.0 / ((double)c->H * (double)c->W);
     a.H = c->H; a.W = c->W; a.h = c->h; a.i0 = c->i0;
@@ -808,8 +809,8 @@ static int prepare_sparse(slmgs_ctx* c, const slmgs_params* params, int n_iter) 
     for (int i = 0; i < n_iter; ++i) {
         const slmgs_params* p = params + i;
         if (p->mraf && p->zero_weights) return 0;   // farfield[zero] = zero_weights: dense by construction
-        if (p->update_weights && p->feedback == 0 && p->mraf)
-            return 0;                               // MRAF + pixel feedback: a global sum over |farfield| needs every tile
+        if (p->update_weights && p->feedback == 0 && p->mraf && p->method == SLMGS_WGS_NOGRETTE)
+            return 0;                               // MRAF + Nogrette takes the element-wise route over every pixel
         // WGS-Nogrette's mean runs over the whole far field, but the ratio is exactly 1 wherever the target is zero:
         // tiles with a non-zero target stay active and the others are counted analytically
         if (p->update_weights && p->feedback == 0 && p->method == SLMGS_WGS_NOGRETTE) nogrette = 1;
@@ -952,6 +953,18 @@ static int run_impl(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
         // WGS-Nogrette needs mean(ratio) over the whole far field before any weight changes (:1851-1852): a forward
         // column pre-pass accumulates the sum of the ratio (no stores), the fused kernel then updates with that mean
         auto needs_ratio = [&](const slmgs_params* p) { return in_kernel_update(p) && p->method == SLMGS_WGS_NOGRETTE; };
+        // MRAF + WGS with pixel feedback: the noise region passes the field through, so the weights must carry their
+        // final normalisation inside the same iteration; a forward column pre-pass accumulates sum(w_new^2)
+        auto mraf_fused = [&](const slmgs_params* p) {
+            return p->update_weights && p->feedback == 0 && p->mraf && !p->zero_weights &&
+                   (p->method == SLMGS_WGS_LEONARDO || p->method == SLMGS_WGS_KIM || p->method == SLMGS_WGS_WU ||
+                    p->method == SLMGS_WGS_TANH);
+        };
+        auto presum_slot = [&](const slmgs_params* p) -> double* {
+            if (needs_ratio(p)) return c->acc + ACC_MEAN;
+            if (mraf_fused(p)) return c->acc + ACC_TMP;
+            return nullptr;
+        };
         // the accumulator slot that receives sum(w^2) alternates; the row kernel that precedes a column kernel
         // clears that kernel's slot (no memset node between the kernels)
         auto out_slot_after = [&](int pending) { return pending == ACC_W0 ? ACC_W1 : ACC_W0; };
@@ -963,25 +976,31 @@ static int run_impl(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
             r.win_dst = c->w_pending >= 0 ? c->winf : nullptr;
         };
         set_win(ra);
-        if (needs_ratio(params)) ra.zero_acc2 = c->acc + ACC_MEAN;
+        ra.zero_acc2 = presum_slot(params);
         if ((e = run_row(c, ROW_FIRST, ra))) return e;
         for (int i = 0; i < n_iter; ++i) {
             const slmgs_params* p = params + i;
             ColArgs ca = col_args(c);
             apply_params(ca, p);
-            const bool in_kernel = in_kernel_update(p);
+            const bool fused_mraf = mraf_fused(p);
+            const bool in_kernel = in_kernel_update(p) || fused_mraf;
             const bool need_amp = p->update_weights && !in_kernel;
             const bool need_phase = ca.phase_mode == PHASE_COMPUTE_STORE;
             const bool need_ratio = needs_ratio(p);
             if (need_ratio) ca.ratio_slot = ACC_MEAN;  // cleared by the row kernel in front of this iteration
-            if (need_amp || need_phase || need_ratio) {
+            if (need_amp || need_phase || need_ratio || fused_mraf) {
                 // one forward column pass for |farfield| (global-dependency updates: Nogrette mean, per-spot
                 // windows, MRAF + WGS) and/or angle(farfield) (the WGS-Kim iteration that fixes the phase)
                 ColArgs fa = col_args(c);
                 fa.store_ampff = need_amp;
                 fa.store_phaseff = need_phase;
-                if (need_ratio) {
-                    fa.ratio_slot = ACC_MEAN;
+                if (need_ratio || fused_mraf) {
+                    if (need_ratio) fa.ratio_slot = ACC_MEAN;
+                    if (fused_mraf) {
+                        fa.wsq_slot = ACC_TMP;
+                        fa.w_in_slot = c->w_pending;
+                        fa.win_f = c->winf;
+                    }
                     fa.wgs.method = p->method;
                     fa.wgs.p = p->feedback_exponent;
                     fa.wgs.f = p->feedback_factor;
@@ -997,14 +1016,15 @@ static int run_impl(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
             ca.wgs_update = in_kernel ? 1 : 0;
             ca.w_in_slot = c->w_pending;
             ca.win_f = c->winf;
-            if (ca.wgs_update) ca.w_out_slot = out_slot_after(c->w_pending);
+            if (ca.wgs_update && !fused_mraf) ca.w_out_slot = out_slot_after(c->w_pending);
+            if (fused_mraf) ca.wsq_slot = ACC_TMP;
             if ((e = run_col(c, COL_FUSED, ca))) return e;
-            if (ca.wgs_update) c->w_pending = ca.w_out_slot;
+            if (ca.wgs_update) c->w_pending = fused_mraf ? -1 : ca.w_out_slot;
             ra.store_phase = (i == n_iter - 1);
             ra.zero_acc = nullptr;
             if (i + 1 < n_iter && in_kernel_update(params + i + 1)) ra.zero_acc = c->acc + out_slot_after(c->w_pending);
             set_win(ra);
-            ra.zero_acc2 = (i + 1 < n_iter && needs_ratio(params + i + 1)) ? c->acc + ACC_MEAN : nullptr;
+            ra.zero_acc2 = (i + 1 < n_iter) ? presum_slot(params + i + 1) : nullptr;
             if ((e = run_row(c, ROW_FUSED, ra))) return e;
         }
     }

@@ -85,9 +85,12 @@ SLMGS_DEVICE float fast_rsqrt(float x) {
 }
 SLMGS_DEVICE float fast_exp(float x) { return __expf(x); }
 SLMGS_DEVICE float fast_tanh(float x) {
-    x = fminf(fmaxf(x, -15.0f), 15.0f);
-    const float e = __expf(2.0f * x);
-    return __fdividef(e - 1.0f, e + 1.0f);
+    const float c = fminf(fmaxf(x, -15.0f), 15.0f);  // (drops a NaN: restored below)
+    const float e = __expf(2.0f * c);
+    const float r = __fdividef(e - 1.0f, e + 1.0f);
+    // a NaN must survive: with an MRAF target the additive methods see T = NaN in the noise region and the reference
+    // ends up with nan_to_num(0 * NaN) = 1e-4 there (_hologram.py:1834-1835, :1870-1873)
+    return (x != x) ? x : r;
 }
 SLMGS_DEVICE void fast_sincos(float x, float* s, float* c) { __sincosf(x, s, c); }
 #else
@@ -473,6 +476,10 @@ struct ColArgs {
     int store_ampff, store_phaseff, store_farfield;  // COL_FWD outputs
     int ratio_slot;       // COL_FWD: accumulate sum(wgs_ratio(|F| / ||F||, target)) here (WGS-Nogrette's mean, :1851-1852), or -1
                           // COL_FUSED: Nogrette mean = (acc[ratio_slot] + ratio_extra) * inv_npix, or -1
+    int wsq_slot;         // MRAF + WGS in the fused loop (the noise region fixes the scale of the weights, so their
+                          // normalisation cannot be deferred, :1877 before :1643-1653).  COL_FWD: accumulate
+                          // sum(w_new^2) of the updated (not stored) weights here; COL_FUSED: scale the updated
+                          // weights by 1 / sqrt(acc[wsq_slot]) at once.  -1 = off
     double ratio_extra;   // added to the sum (pixels that were not visited and whose ratio is known to be 1), normally 0
     double inv_npix;      // 1 / (H W)
     int pdl;              // launch with programmatic dependent launch
@@ -600,6 +607,26 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
             }
             accum_add(a.acc + (long long)id.by * a.acc_bs + a.ratio_slot, rs);
         }
+        if (a.wsq_slot >= 0) {  // pre-pass of MRAF + WGS: the update exactly as the fused kernel will apply it
+            double* acc = a.acc + (long long)id.by * a.acc_bs;
+            float win = 1.0f;
+            if (a.w_in_slot >= 0) win = a.win_f ? __ldg(a.win_f + id.by) : (float)(1.0 / sqrt(acc[a.w_in_slot]));
+            double ws = 0.0;
+            SLMGS_UNROLL
+            for (int u = 0; u < E / R; ++u) {
+                SLMGS_UNROLL
+                for (int m = 0; m < R; ++m) {
+                    const long long off = (long long)F::last_index(L.lt + F::TPL * u, m) * L.C;
+                    const cf z = st.v[u * R + m];
+                    const float m2 = z.x * z.x + z.y * z.y;
+                    const float famp = (m2 > 1.0e-37f ? m2 * fast_rsqrt(m2) : 0.f) * a.scale;
+                    const float w = wgs_apply(ld_stream(a.weights + L.ibase + off) * win,
+                                              wgs_multiplier_fast(famp, ld_stream(a.target + L.tbase + off), a.wgs));
+                    ws += (double)(w * w);
+                }
+            }
+            accum_add(acc + a.wsq_slot, ws);
+        }
     }
 
     // Far-field constraint (+ fused weight update): _hologram.py:1550-1653.
@@ -677,6 +704,8 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
         const float fscale = SCALED ? 1.0f : a.scale;
         const float lg2s = fast_lg2(fscale * a.wgs.inv_fnorm);
         WgsParams wq_params = a.wgs;
+        float wnorm = 1.0f;
+        if (GEN && !SCALED && a.wsq_slot >= 0) wnorm = (float)(1.0 / sqrt(acc[a.wsq_slot]));
         if (GEN && !SCALED && a.ratio_slot >= 0) {  // WGS-Nogrette in the fused loop: mean of the ratio from the pre-pass
             // sparse far field: the tiles that were not launched hold target == 0 only, where the ratio is exactly 1 (:1841)
             const double skipped = a.tiles ? (double)a.H * (double)(a.W - __ldg(a.tile_count + id.by) * L.C) : 0.0;
@@ -740,6 +769,7 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
                         else fc = wgs_multiplier_fast(famp, t, wq_params);
                     }
                     w = wgs_apply(w, fc);
+                    if (GEN && !SCALED) w *= wnorm;
                     a.weights[L.ibase + off] = w;
                     wsum += w * w;
                 }

@@ -247,3 +247,30 @@ def test_nogrette_sparse_equals_dense(backend):
     assert res[0].sparse_info()[0]
     _same(res[0].weights, res[1].weights, 2e-6)
     _same(res[0].phase, res[1].phase, 2e-5)
+
+
+@pytest.mark.parametrize("method,kw", [("WGS-Leonardo", {}), ("WGS-Kim", {"fix_phase_iteration": 2}),
+                                       ("WGS-Leonardo", {"mraf_factor": 0.6}), ("WGS-tanh", {})])
+def test_mraf_wgs_fused_sparse_equals_dense_and_oracle(method, kw, backend):
+    """MRAF + WGS with pixel feedback runs in the fused loop (sum(w_new^2) pre-pass, immediate normalisation): the
+    noise-region tiles and the tiles with weights are active, everything else is skipped."""
+    rng = np.random.default_rng(12)
+    shape = (64, 256)
+    target = _spot_target(shape, [20, 21, 150, 151], 3, rng)
+    target[10:30, 60:90] = np.nan
+    phase = rng.uniform(-np.pi, np.pi, shape).astype(np.float32)
+    args = dict(target=target, phase=phase)
+    opt = dict(method=method, maxiter=5, **kw)
+    a = _run(args, opt, True)
+    b = _run(args, opt, False)
+    assert a.sparse_info()[0] and not b.sparse_info()[0]
+    _same(a.phase, b.phase, 2e-5)
+    _same(a.amp_ff, b.amp_ff, 2e-6)
+    _same(np.nan_to_num(a.weights), np.nan_to_num(b.weights), 2e-6)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = gs_oracle.OracleHologram(target, phase=phase)
+        ref.optimize(verbose=False, **opt)
+    assert np.linalg.norm(a.amp_ff - ref.amp_ff) / np.linalg.norm(ref.amp_ff) <= 1e-5
+    assert np.linalg.norm(a.weights - ref.weights) / np.linalg.norm(ref.weights) <= 1e-5
+    assert bool(a.flags["fixed_phase"]) == bool(ref.flags["fixed_phase"])

@@ -88,3 +88,106 @@ def test_random_case_matches_oracle(seed, backend):
     i0, i1, i2, i3 = gs_oracle.crop_bounds(b.shape, b.slm_shape)
     ok = nf[i0:i1, i2:i3] > 1e-4 * nf.max()
     assert np.sqrt(np.mean(dphi[ok] ** 2)) <= 2e-5 * loose, info
+
+
+def make_spot_case(seed):
+    rng = np.random.default_rng(5000 + seed)
+    H, W = int(rng.choice([32, 64, 128, 256])), int(rng.choice([32, 64, 128, 256]))
+    n = int(rng.integers(2, min(25, H - 12, W - 12)))
+    # distinct integer-ish positions away from the border (the integration windows must fit)
+    xs = rng.choice(np.arange(6, W - 6), size=n, replace=False).astype(float) + rng.uniform(-0.3, 0.3, n)
+    ys = rng.choice(np.arange(6, H - 6), size=n, replace=False).astype(float) + rng.uniform(-0.3, 0.3, n)
+    method = ["GS", "WGS-Leonardo", "WGS-Kim", "WGS-Nogrette", "WGS-Wu", "WGS-tanh"][int(rng.integers(6))]
+    feedback = ["computational_spot", "computational"][int(rng.integers(2))]
+    kw = {}
+    if method == "WGS-Kim":
+        kw["fix_phase_iteration"] = int(rng.integers(1, 4))
+    ctor = {}
+    if rng.random() < 0.3:
+        k = int(rng.integers(1, 4))
+        ctor["null_vectors"] = np.vstack([rng.uniform(8, W - 8, k), rng.uniform(8, H - 8, k)])
+        ctor["null_radius"] = int(rng.integers(1, 4))
+    if rng.random() < 0.5:
+        ctor["spot_amp"] = rng.uniform(0.5, 1.5, n)
+    padded = rng.random() < 0.4
+    slm = (int(rng.integers(H // 2, H + 1)), int(rng.integers(W // 2, W + 1))) if padded else (H, W)
+    phase = rng.uniform(-np.pi, np.pi, slm).astype(np.float32)
+    return dict(shape=(H, W), v=np.vstack([xs, ys]), method=method, feedback=feedback, kw=kw, ctor=ctor, slm=slm,
+                phase=phase, maxiter=int(rng.integers(2, 6)))
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_random_spot_case_matches_oracle(seed, backend):
+    from slmsuite_b200 import SpotHologram
+
+    c = make_spot_case(seed)
+    out = []
+    for cls in (SpotHologram, gs_oracle.OracleSpotHologram):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ctor = {k: (np.array(v, copy=True) if isinstance(v, np.ndarray) else v) for k, v in c["ctor"].items()}
+            h = cls(c["shape"], c["v"].copy(), basis="knm", slm_shape=c["slm"], phase=c["phase"], **ctor)
+            h.optimize(c["method"], maxiter=c["maxiter"], verbose=False, feedback=c["feedback"], **c["kw"])
+        out.append(h)
+    a, b = out
+    info = (seed, c["shape"], c["slm"], c["method"], c["feedback"], sorted(c["ctor"]), c["maxiter"], a.sparse_info())
+    assert a.spot_integration_width_knm == b.spot_integration_width_knm, info
+    assert rel_rmse(a.amp_ff, b.amp_ff) <= 1e-5, info
+    assert rel_rmse(a.weights, b.weights) <= 1e-5, info
+    assert bool(a.flags.get("fixed_phase", False)) == bool(b.flags.get("fixed_phase", False)), info
+    dphi = np.angle(np.exp(1j * (a.phase.astype(np.float64) - b.phase.astype(np.float64))))
+    assert np.sqrt(np.mean(dphi ** 2)) <= 2e-5, info
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_compressed_case_matches_oracle(seed, backend):
+    from oracle import compressed_oracle
+    from slmsuite_b200 import CompressedSpotHologram
+
+    rng = np.random.default_rng(9000 + seed)
+    h, w = int(rng.integers(24, 97)), int(rng.integers(24, 97))
+    yy, xx = np.mgrid[0:h, 0:w]
+    grid = ((xx - w / 2) * 12.6, (yy - h / 2) * 12.6)
+    scaling = 1.0 / float(rng.uniform(300, 900))
+    n = int(rng.integers(2, 30))  # (one spot: the reference's set_target squeezes the vector to 0-d and raises, _spots.py:935-940)
+    kind = int(rng.integers(4))
+    if kind == 0:
+        basis, v = "kxy", rng.uniform(-0.03, 0.03, (2, n))
+    elif kind == 1:
+        basis, v = "kxy", np.vstack([rng.uniform(-0.03, 0.03, (2, n)), rng.uniform(-2e-4, 2e-4, (1, n))])
+    elif kind == 2:
+        basis, v = "zernike", np.vstack([rng.uniform(-25, 25, (2, n)), rng.uniform(-3, 3, (2, n))])  # [2, 1, 4, 3]
+    else:
+        basis = [1, 2, 5, 7, 8, 9, 12]  # x and y anywhere in the list, coma, trefoil, spherical
+        v = np.vstack([rng.uniform(-20, 20, (2, n)), rng.uniform(-1, 1, (5, n))])
+    amp_n = rng.uniform(0.5, 1.5, n)
+    if n >= 4 and rng.random() < 0.5:
+        amp_n[int(rng.integers(n))] = np.nan
+        amp_n[int(rng.integers(n))] = 0.0
+        if not np.any(np.nan_to_num(amp_n) > 0):
+            amp_n[0] = 1.0
+    method = METHODS[int(rng.integers(len(METHODS)))]
+    kw = {"fix_phase_iteration": int(rng.integers(1, 4))} if method == "WGS-Kim" else {}
+    if np.any(np.isnan(amp_n)) and rng.random() < 0.5:
+        kw["mraf_factor"] = float(rng.uniform(0.3, 1.0))
+    src = np.exp(-((xx - w / 2) ** 2 + (yy - h / 2) ** 2) / (0.4 * h * w)) if rng.random() < 0.5 else None
+    args = dict(basis=basis, spot_amp=amp_n, slm_grid=grid, zernike_scaling=scaling, amp=src,
+                phase=rng.uniform(-np.pi, np.pi, (h, w)).astype(np.float32))
+    maxiter = int(rng.integers(1, 6))
+    out = []
+    for cls in (CompressedSpotHologram, compressed_oracle.OracleCompressedSpotHologram):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            a = {k: (np.array(x, copy=True) if isinstance(x, np.ndarray) else x) for k, x in args.items()}
+            o = cls(v.copy(), **a)
+            o.optimize(method, maxiter=maxiter, verbose=False, **kw)
+        out.append(o)
+    a, b = out
+    info = (seed, (h, w), n, basis, method, maxiter, kw)
+    assert rel_rmse(a.amp_ff, b.amp_ff) <= 1e-5, info
+    assert rel_rmse(a.weights, b.weights) <= 1e-5, info
+    assert bool(a.flags.get("fixed_phase", False)) == bool(b.flags.get("fixed_phase", False)), info
+    dphi = np.angle(np.exp(1j * (a.phase.astype(np.float64) - b.phase.astype(np.float64))))
+    nf = np.abs(b.nearfield)
+    ok = nf > 1e-4 * nf.max()
+    assert np.sqrt(np.mean(dphi[ok] ** 2)) <= 1e-4, info

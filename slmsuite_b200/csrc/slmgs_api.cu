@@ -584,7 +584,13 @@ extern "C" int slmgs_reset_weights(slmgs_ctx* c) {
     ElemArgs a = elem_args(c, c->target, c->weights, P);
     a.src_bs = c->target_shared ? 0 : P;
     c->w_pending = -1;
-    c->tiles_dirty = true;
+    if (!c->tiles_dirty && !c->tile_flags_h.empty()) {
+        // weights := nan_to_num(target): their occupancy is the target's (flag bit 2), already known -- no device pass
+        for (int& f : c->tile_flags_h) f = (f & ~1) | ((f & 4) ? 1 : 0);
+        c->tile_key = -1;
+    } else {
+        c->tiles_dirty = true;
+    }
     if (c->zero_w) RT(c, rt_memset(c->zero_w, 0, (size_t)c->B * P * sizeof(cf), c->stream));  // zero_weights *= 0, :609-610
     return launch_elem<EW_FILL_NAN0>(c, a, c->B);
 }

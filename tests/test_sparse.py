@@ -274,3 +274,27 @@ def test_mraf_wgs_fused_sparse_equals_dense_and_oracle(method, kw, backend):
     assert np.linalg.norm(a.amp_ff - ref.amp_ff) / np.linalg.norm(ref.amp_ff) <= 1e-5
     assert np.linalg.norm(a.weights - ref.weights) / np.linalg.norm(ref.weights) <= 1e-5
     assert bool(a.flags["fixed_phase"]) == bool(ref.flags["fixed_phase"])
+
+
+def test_reset_weights_restores_the_target_occupancy(backend):
+    """reset_weights() sets weights = nan_to_num(target): the tile list falls back to the target's occupancy without a
+    new device pass, and the next run equals a fresh hologram's."""
+    rng = np.random.default_rng(13)
+    shape = (64, 256)
+    target = _spot_target(shape, [10, 200], 2, rng)
+    phase = rng.uniform(-np.pi, np.pi, shape).astype(np.float32)
+    w = np.zeros(shape, dtype=np.float32)
+    w[5, 100] = 1.0
+    w[7, 130] = 1.0
+    w[9, 60] = 1.0
+    h = _run(dict(target=target, phase=phase), dict(method="WGS-Leonardo", maxiter=3), True, weights=w)
+    n_custom = h.sparse_info()[1]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        h.reset_phase(phase)
+        h.reset(reset_phase=False)
+        h.optimize("WGS-Leonardo", maxiter=3, verbose=False)
+    fresh = _run(dict(target=target, phase=phase), dict(method="WGS-Leonardo", maxiter=3), True)
+    assert h.sparse_info()[0] and h.sparse_info()[1] == fresh.sparse_info()[1] <= 2 < n_custom
+    _same(h.phase, fresh.phase, 2e-5)
+    _same(h.weights, fresh.weights, 2e-6)

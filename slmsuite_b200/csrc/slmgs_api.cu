@@ -1564,6 +1564,9 @@ struct slmgs_comp {
     float *phase, *amp, *target, *weights, *amp_ff, *phase_ff;
     cf *nf, *far, *far_norm;
     float amp_scalar;
+#ifndef SLMGS_EMULATE
+    cudaEvent_t t0, t1;
+#endif
 };
 
 static std::string g_comp_error;
@@ -1595,6 +1598,10 @@ extern "C" int slmgs_comp_destroy(slmgs_comp* c) {
                     c->nf, c->far, c->far_norm};
     for (void* p : ptrs)
         if (p) rt_free(p);
+#ifndef SLMGS_EMULATE
+    if (c->t0) cudaEventDestroy(c->t0);
+    if (c->t1) cudaEventDestroy(c->t1);
+#endif
     if (c->stream) rt_stream_destroy(c->stream);
     delete c;
     return SLMGS_OK;
@@ -1619,6 +1626,9 @@ extern "C" int slmgs_comp_create(slmgs_comp** out, int device, int h, int w, int
     c->mono = c->cw = c->facc = nullptr;
     c->phase = c->amp = c->target = c->weights = c->amp_ff = c->phase_ff = nullptr;
     c->nf = c->far = c->far_norm = nullptr;
+#ifndef SLMGS_EMULATE
+    c->t0 = c->t1 = nullptr;
+#endif
     const size_t S = (size_t)c->S, N = (size_t)n_spots;
     int err = 0;
     void* p;
@@ -1803,12 +1813,17 @@ extern "C" int slmgs_comp_run(slmgs_comp* c, const slmgs_params* params, int n_i
 extern "C" int slmgs_comp_timer(slmgs_comp* c, int start, float* ms) {
     CHECK_COMP(c);
 #ifndef SLMGS_EMULATE
-    static thread_local cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (!e0) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
-    if (start) return (int)cudaEventRecord(e0, c->stream) ? SLMGS_ERR_CUDA : SLMGS_OK;
-    cudaEventRecord(e1, c->stream);
-    cudaEventSynchronize(e1);
-    if (ms) cudaEventElapsedTime(ms, e0, e1);
+    if (!c->t0) {
+        CRT(c, (int)cudaEventCreate(&c->t0));
+        CRT(c, (int)cudaEventCreate(&c->t1));
+    }
+    if (start) {
+        CRT(c, (int)cudaEventRecord(c->t0, c->stream));
+        return SLMGS_OK;
+    }
+    CRT(c, (int)cudaEventRecord(c->t1, c->stream));
+    CRT(c, (int)cudaEventSynchronize(c->t1));
+    if (ms) CRT(c, (int)cudaEventElapsedTime(ms, c->t0, c->t1));
 #else
     if (ms) *ms = 0.f;
     (void)start;

@@ -219,6 +219,16 @@ SLMGS_API int slmgs_comp_get_amp_ff(slmgs_comp*, float* amp_ff);
 SLMGS_API int slmgs_comp_get_farfield(slmgs_comp*, float* farfield_c64);                 /* [N] interleaved re/im, normalised (:822) */
 SLMGS_API int slmgs_comp_forward(slmgs_comp*, int populate);                              /* _nearfield2farfield :677-708 + amp_ff; populate: also phase_ff (_populate_results) */
 SLMGS_API int slmgs_comp_run(slmgs_comp*, const slmgs_params* params, int n_iter, int populate); /* optimize_gs with the compressed maps */
+/* The loop in pieces, for ONE hologram whose pixels are sharded over several GPUs (each rank: a context over its slab
+ * of SLM rows, all N spots).  near -> far sums over pixels, so the accumulators are partial sums: all-reduce the
+ * [N][2] float64 buffer at slmgs_comp_facc_ptr (16 N bytes) between slmgs_comp_near2far and
+ * slmgs_comp_constrain_far2near (or slmgs_comp_finalize for a forward / _populate_results); every rank then runs the
+ * identical N-vector stage and projects its own slab. */
+SLMGS_API int slmgs_comp_near2far(slmgs_comp*);
+SLMGS_API void* slmgs_comp_facc_ptr(slmgs_comp*);
+SLMGS_API void* slmgs_comp_stream(slmgs_comp*);
+SLMGS_API int slmgs_comp_constrain_far2near(slmgs_comp*, const slmgs_params*);
+SLMGS_API int slmgs_comp_finalize(slmgs_comp*, int populate);
 SLMGS_API int slmgs_comp_timer(slmgs_comp*, int start, float* ms);                        /* CUDA events on the context's stream */
 
 #ifdef __cplusplus

@@ -124,6 +124,11 @@ SIGNATURES = {
     "slmgs_comp_get_farfield": (C.c_int, [_ctx, _fp]),
     "slmgs_comp_forward": (C.c_int, [_ctx, C.c_int]),
     "slmgs_comp_run": (C.c_int, [_ctx, _pp, C.c_int, C.c_int]),
+    "slmgs_comp_near2far": (C.c_int, [_ctx]),
+    "slmgs_comp_facc_ptr": (C.c_void_p, [_ctx]),
+    "slmgs_comp_stream": (C.c_void_p, [_ctx]),
+    "slmgs_comp_constrain_far2near": (C.c_int, [_ctx, _pp]),
+    "slmgs_comp_finalize": (C.c_int, [_ctx, C.c_int]),
     "slmgs_comp_timer": (C.c_int, [_ctx, C.c_int, _fp]),
 }
 

@@ -414,3 +414,176 @@ class CompressedSpotHologram(Hologram):
             self._check(self._lib.slmgs_comp_forward(self._ctx, 1))
         self._amp_ff_set = True
         self._phase_ff_none = False
+
+
+# --------------------------------------------------------------------------- one hologram on several GPUs
+class TorchComm:
+    """
+    The two collectives a pixel-sharded compressed hologram needs, over ``torch.distributed`` (NCCL between GPUs; gloo
+    for the CPU test-suite, where the "device" buffers of the emulation library are host memory).  Plumbing only.
+    """
+
+    def __init__(self, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def allreduce_f64(self, ptr, count, on_device, device):
+        """In-place sum over ranks of ``count`` float64 values at ``ptr``."""
+        torch = self.torch
+        if on_device:
+            class _Dev:
+                __cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+
+            t = torch.as_tensor(_Dev(), device=torch.device("cuda", device))
+            self.dist.all_reduce(t, group=self.group)
+            torch.cuda.current_stream(device).synchronize()
+        else:
+            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(count,))
+            t = torch.from_numpy(a)
+            self.dist.all_reduce(t, group=self.group)
+
+    def allgather_rows(self, local, rows_per_rank, on_device, device):
+        """Concatenate the row slabs of every rank (slabs may differ in height)."""
+        torch = self.torch
+        hmax = max(rows_per_rank)
+        pad = np.zeros((hmax,) + local.shape[1:], dtype=local.dtype)
+        pad[:local.shape[0]] = local
+        t = torch.from_numpy(pad)
+        if on_device:
+            t = t.cuda(device)
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t, group=self.group)
+        return np.concatenate([o.cpu().numpy()[:r] for o, r in zip(out, rows_per_rank)], axis=0)
+
+
+class ShardedCompressedSpotHologram(CompressedSpotHologram):
+    """
+    ONE compressed spot hologram spread over several GPUs (not in the reference, whose kernels are single-GPU).
+
+    The SLM rows are split into contiguous slabs, one per rank; every rank knows all N spots.  near -> far is a sum
+    over pixels, so after the local pass the ranks all-reduce the N complex accumulators (16 N bytes -- the only
+    exchange of an iteration), run the identical N-vector stage (normalisation, WGS update, WGS-Kim phase, MRAF) and
+    project their own slab.  ``phase`` / ``get_phase()`` gather the slabs.  Same constructor as
+    ``CompressedSpotHologram`` plus ``comm`` (default: ``TorchComm()`` on the default process group).
+    """
+
+    def __init__(self, spot_vectors, basis="kxy", spot_amp=None, cameraslm=None, cuda=False, slm_grid=None,
+                 zernike_scaling=None, amp=None, phase=None, device=0, comm=None, **kwargs):
+        self._comm = comm if comm is not None else TorchComm()
+        rank, world = self._comm.rank, self._comm.world
+        if cameraslm is not None:
+            slm = cameraslm.slm if hasattr(cameraslm, "slm") else cameraslm
+            slm_grid = slm.grid
+            if zernike_scaling is None:
+                zernike_scaling = slm.get_source_zernike_scaling()
+            if amp is None and hasattr(slm, "_get_source_amplitude"):
+                amp = slm._get_source_amplitude()
+        if slm_grid is None:
+            raise ValueError("cameraslm must be passed.")
+        x_grid, y_grid = (np.asarray(g) for g in slm_grid)
+        full = tuple(int(s) for s in x_grid.shape)
+        bounds = [(full[0] * r) // world for r in range(world + 1)]
+        self._rows = [bounds[r + 1] - bounds[r] for r in range(world)]
+        if min(self._rows) < 1:
+            raise ValueError("more ranks than SLM rows")
+        r0, r1 = bounds[rank], bounds[rank + 1]
+        self._r0, self._r1, self._full_shape = r0, r1, full
+        if amp is not None:  # the reference normalises over the whole SLM (_hologram.py:404-405): do it before slicing
+            amp = np.array(amp, dtype=np.float32)
+            amp *= 1 / _norm(amp)
+            amp = np.ascontiguousarray(amp[r0:r1])
+        if phase is not None:
+            phase = np.asarray(phase)[r0:r1]
+        super().__init__(spot_vectors, basis=basis, spot_amp=spot_amp, cameraslm=None, cuda=cuda,
+                         slm_grid=(x_grid[r0:r1], y_grid[r0:r1]), zernike_scaling=zernike_scaling, amp=amp, phase=phase,
+                         device=device, **kwargs)
+        self.cameraslm = cameraslm
+        if amp is None:
+            # scalar amplitude 1/sqrt(h w) of the WHOLE SLM (the constructor took the slab's size)
+            self._amp = 1 / np.sqrt(np.prod(full))
+            self._check(self._lib.slmgs_comp_set_amp_scalar(self._ctx, float(self._amp)))
+        else:
+            # undo the slab-local renormalisation of the base constructor
+            self._amp = amp
+            self._check(self._lib.slmgs_comp_set_amp_array(self._ctx, _lib.fptr(_lib.f32(amp))))
+        self._local_shape = tuple(self.slm_shape)
+        self.slm_shape = self.shape = full  # the public shape is the whole SLM; the device holds this rank's slab
+        self._on_device = _lib.library_path() == _lib.DEFAULT_LIBRARY
+
+    # the slab is what the device holds; the public shape is the whole SLM
+    @property
+    def phase(self):
+        local = np.empty(self._local_shape, dtype=np.float32)
+        self._check(self._lib.slmgs_comp_get_phase(self._ctx, _lib.fptr(local)))
+        return self._comm.allgather_rows(local, self._rows, self._on_device, self._device)
+
+    @phase.setter
+    def phase(self, value):
+        self.reset_phase(value)
+
+    def reset_phase(self, custom_phase=None, random_phase=None, quadratic_phase=None):
+        """_hologram.py:536-601; ``custom_phase`` has the shape of the whole SLM (or of this rank's slab)."""
+        local = getattr(self, "_local_shape", None) or tuple(self.slm_shape)
+        if custom_phase is not None:
+            p = np.array(custom_phase, dtype=self.dtype)
+            if tuple(p.shape) == tuple(getattr(self, "_full_shape", ())) and tuple(p.shape) != tuple(local):
+                p = p[self._r0:self._r1]
+            if tuple(p.shape) != tuple(local):
+                raise ValueError(f"Reset phase of shape {p.shape} is not of slm_shape {self._full_shape}")
+        else:
+            if quadratic_phase or self.flags.get("quadratic_phase", False):
+                raise NotImplementedError("quadratic_phase preconditioning is outside the GS/WGS hot path; pass phase=")
+            if random_phase is None:
+                random_phase = self.flags.get("random_phase", 1)
+            p = np.zeros(local, dtype=self.dtype)
+            if random_phase:
+                p += random_phase * np.random.default_rng().uniform(-np.pi, np.pi, local).astype(self.dtype)
+        self._check(self._lib.slmgs_comp_set_phase(self._ctx, _lib.fptr(_lib.f32(np.ascontiguousarray(p)))))
+        self._phase_set = True
+        self._amp_ff_set = False
+
+    @property
+    def nearfield(self):
+        raise NotImplementedError("the near field of a sharded hologram lives in slabs; use .phase")
+
+    def _reduce(self):
+        self._check(self._lib.slmgs_comp_sync(self._ctx))
+        self._comm.allreduce_f64(self._lib.slmgs_comp_facc_ptr(self._ctx), 2 * len(self), self._on_device, self._device)
+
+    def _forward(self, populate):
+        self._check(self._lib.slmgs_comp_near2far(self._ctx))
+        self._reduce()
+        self._check(self._lib.slmgs_comp_finalize(self._ctx, 1 if populate else 0))
+
+    @property
+    def farfield(self):
+        if not self._amp_ff_set:
+            self._forward(False)
+            self._amp_ff_set = True
+        return self._vec(self._lib.slmgs_comp_get_farfield, np.complex64)
+
+    def optimize_gs(self, iterations, callback):
+        """_hologram.py:1427-1493 with the compressed maps, the pixel sum completed by one all-reduce per iteration."""
+        self._check_spot_zernike_change()
+        mraf = self._mraf_enabled()
+        if "WGS" in self.flags["method"]:
+            self._check_feedback()
+        for _ in iterations:
+            if callback is not None:
+                self._forward(False)
+                self._amp_ff_set = True
+                if callback(self):
+                    break
+            self._update_stats(self.flags["stat_groups"])
+            params = self._iteration_params(mraf, stepped=callback is not None)
+            self._check(self._lib.slmgs_comp_near2far(self._ctx))
+            self._reduce()
+            self._check(self._lib.slmgs_comp_constrain_far2near(self._ctx, C.byref(params)))
+            self.iter += 1
+        self._forward(True)
+        self._amp_ff_set = True
+        self._phase_ff_none = False

@@ -1786,6 +1786,40 @@ extern "C" int slmgs_comp_forward(slmgs_comp* c, int populate) {
     return comp_vec(c, nullptr, populate ? 2 : 1);
 }
 
+// ---- the same loop in pieces, for a hologram whose PIXELS are sharded over several GPUs ---------------------------
+// Each rank holds a slab of SLM rows (its own context with S_local pixels, all N spots).  near -> far is a sum over
+// pixels, so the per-rank accumulators are partial sums: the caller all-reduces the [N][2] float64 buffer
+// (slmgs_comp_facc_ptr, 16 N bytes) between slmgs_comp_near2far and slmgs_comp_constrain_far2near; every rank then
+// runs the identical N-vector stage and projects its own slab.  One tiny collective per iteration, nothing else.
+extern "C" void* slmgs_comp_facc_ptr(slmgs_comp* c) { return c ? (void*)c->facc : nullptr; }
+extern "C" void* slmgs_comp_stream(slmgs_comp* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" int slmgs_comp_near2far(slmgs_comp* c) {
+    CHECK_COMP(c);
+    return comp_near2far(c);
+}
+extern "C" int slmgs_comp_finalize(slmgs_comp* c, int populate) {
+    CHECK_COMP(c);
+    return comp_vec(c, nullptr, populate ? 2 : 1);
+}
+static int comp_check_params(slmgs_comp* c, const slmgs_params* p) {
+    if (!p) return cfail(c, SLMGS_ERR_INVALID, "params is NULL");
+    if (p->method < SLMGS_GS || p->method > SLMGS_WGS_TANH) return cfail(c, SLMGS_ERR_INVALID, "unknown method");
+    if (p->phase_mode < 0 || p->phase_mode > 2) return cfail(c, SLMGS_ERR_INVALID, "unknown phase_mode");
+    if (p->update_weights && p->method == SLMGS_GS) return cfail(c, SLMGS_ERR_INVALID, "GS has no weight update");
+    if (p->mraf && p->zero_weights) return cfail(c, SLMGS_ERR_INVALID, "the MRAF zero_factor accumulator is not supported for compressed holograms");
+    return 0;
+}
+extern "C" int slmgs_comp_constrain_far2near(slmgs_comp* c, const slmgs_params* p) {
+    CHECK_COMP(c);
+    int e;
+    if ((e = comp_check_params(c, p))) return e;
+    if ((e = comp_vec(c, p, 0))) return e;
+    CompArgs a = comp_args(c);
+    const long long span = 256LL * COMP_PPT;
+    CRT(c, comp_launch_mt<CompFar2NearKernel>(c, (int)((c->S + span - 1) / span), 1, a));
+    return SLMGS_OK;
+}
+
 // optimize_gs for the compressed maps: n_iter iterations (+ _populate_results)
 extern "C" int slmgs_comp_run(slmgs_comp* c, const slmgs_params* params, int n_iter, int populate) {
     CHECK_COMP(c);

@@ -11,7 +11,7 @@ from .spots import SpotHologram
 from .batch import HologramBatch, optimize_sharded, shard_bounds
 from .multiplane import MultiplaneHologram
 from .camera import SimulatedCamera
-from .compressed import CompressedSpotHologram
+from .compressed import CompressedSpotHologram, ShardedCompressedSpotHologram
 
-__all__ = ["Hologram", "SpotHologram", "HologramBatch", "MultiplaneHologram", "SimulatedCamera", "CompressedSpotHologram", "optimize_sharded", "shard_bounds", "ALGORITHM_DEFAULTS", "ALGORITHM_INDEX", "FEEDBACK_OPTIONS"]
+__all__ = ["Hologram", "SpotHologram", "HologramBatch", "MultiplaneHologram", "SimulatedCamera", "CompressedSpotHologram", "ShardedCompressedSpotHologram", "optimize_sharded", "shard_bounds", "ALGORITHM_DEFAULTS", "ALGORITHM_INDEX", "FEEDBACK_OPTIONS"]
 __version__ = "0.1.0"

@@ -431,16 +431,22 @@ class TorchComm:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
 
-    def allreduce_f64(self, ptr, count, on_device, device):
-        """In-place sum over ranks of ``count`` float64 values at ``ptr``."""
+    def allreduce_f64(self, ptr, count, on_device, device, stream_ptr=None):
+        """In-place sum over ranks of ``count`` float64 values at ``ptr``.  On the device the collective is ordered
+        on the library's own stream (``torch.cuda.ExternalStream``): the process group waits for that stream's
+        pending kernels and the stream waits for the collective -- no host synchronisation."""
         torch = self.torch
         if on_device:
             class _Dev:
                 __cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
 
             t = torch.as_tensor(_Dev(), device=torch.device("cuda", device))
-            self.dist.all_reduce(t, group=self.group)
-            torch.cuda.current_stream(device).synchronize()
+            if stream_ptr:
+                with torch.cuda.stream(torch.cuda.ExternalStream(int(stream_ptr), device=torch.device("cuda", device))):
+                    self.dist.all_reduce(t, group=self.group)
+            else:
+                self.dist.all_reduce(t, group=self.group)
+                torch.cuda.current_stream(device).synchronize()
         else:
             a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(count,))
             t = torch.from_numpy(a)
@@ -551,8 +557,10 @@ class ShardedCompressedSpotHologram(CompressedSpotHologram):
         raise NotImplementedError("the near field of a sharded hologram lives in slabs; use .phase")
 
     def _reduce(self):
-        self._check(self._lib.slmgs_comp_sync(self._ctx))
-        self._comm.allreduce_f64(self._lib.slmgs_comp_facc_ptr(self._ctx), 2 * len(self), self._on_device, self._device)
+        if not self._on_device:
+            self._check(self._lib.slmgs_comp_sync(self._ctx))
+        self._comm.allreduce_f64(self._lib.slmgs_comp_facc_ptr(self._ctx), 2 * len(self), self._on_device, self._device,
+                                 self._lib.slmgs_comp_stream(self._ctx))
 
     def _forward(self, populate):
         self._check(self._lib.slmgs_comp_near2far(self._ctx))

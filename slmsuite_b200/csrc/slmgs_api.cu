@@ -749,7 +749,7 @@ static int run_col(slmgs_ctx* c, int mode, const ColArgs& a) {
     prof_mark(c, 3 + mode, true);
     // compile-time specialisation of the fused constraint (slmgs_kernels.h, VAR_*)
     int var = VAR_GENERAL;
-    if (mode == COL_FUSED && !a.mraf) {
+    if (mode == COL_FUSED && !a.mraf && a.wsq_slot < 0) {  // (immediate normalisation only exists in the general variant)
         const bool pow_like = a.wgs.method == METHOD_LEONARDO || a.wgs.method == METHOD_KIM;
         if (!a.wgs_update && a.phase_mode == PHASE_COMPUTE) var = VAR_GS;
         else if (a.wgs_update && pow_like && a.phase_mode == PHASE_COMPUTE) var = VAR_POW;
@@ -1305,20 +1305,40 @@ extern "C" int slmgs_run_accumulate(slmgs_ctx* c, const slmgs_params* p, float w
     if (p->update_weights && p->method == SLMGS_GS) return fail(c, SLMGS_ERR_INVALID, "GS has no weight update");
     if (p->update_weights && p->feedback == 1 && c->n_spots < 1)
         return fail(c, SLMGS_ERR_STATE, "spot feedback without slmgs_set_spots");
+    // The children's near fields are SUMMED, so the scale of each child's far field matters: the deferred (one
+    // kernel late) weight normalisation of slmgs_run is not allowed here.  Power-law / Wu / tanh updates with pixel
+    // feedback use the pre-pass scheme of MRAF + WGS instead (a forward column pass accumulates sum(w_new^2), the
+    // fused kernel updates and normalises at once); the others go through the forward pass + update kernels.
+    const bool fused_update = p->update_weights && p->feedback == 0 && !(p->mraf && p->zero_weights) &&
+                              (p->method == SLMGS_WGS_LEONARDO || p->method == SLMGS_WGS_KIM ||
+                               p->method == SLMGS_WGS_WU || p->method == SLMGS_WGS_TANH);
+    const bool need_amp = p->update_weights != 0 && !fused_update;
+    if (!need_amp) {
+        if ((e = prepare_sparse(c, p, 1))) return e;  // (one iteration: the flags persist between calls)
+    } else {
+        c->sparse_now = false;
+    }
+    struct SparseOff {  // the stepped entry points and the getters see the whole far field
+        slmgs_ctx* c;
+        ~SparseOff() { c->last_sparse = c->sparse_now; c->sparse_now = false; }
+    } sparse_off{c};
+    if ((e = resolve_weights(c))) return e;
     RowArgs ra = row_args(c);
+    if (fused_update) ra.zero_acc2 = c->acc + ACC_TMP;
     if ((e = run_row(c, ROW_FIRST, ra))) return e;
     ColArgs ca = col_args(c);
     apply_params(ca, p);
-    // The children's near fields are SUMMED, so the scale of each child's far field matters: the deferred
-    // (one kernel late) weight normalisation of slmgs_run is not allowed here.  Every update goes through the
-    // forward pass + update kernels, which normalise before the constraint.
-    const bool in_kernel = false;
-    const bool need_amp = p->update_weights != 0;
     const bool need_phase = ca.phase_mode == PHASE_COMPUTE_STORE;
-    if (need_amp || need_phase) {
+    if (need_amp || need_phase || fused_update) {
         ColArgs fa = col_args(c);
         fa.store_ampff = need_amp;
         fa.store_phaseff = need_phase;
+        if (fused_update) {
+            fa.wsq_slot = ACC_TMP;
+            fa.wgs.method = p->method;
+            fa.wgs.p = p->feedback_exponent;
+            fa.wgs.f = p->feedback_factor;
+        }
         if ((e = run_col(c, COL_FWD, fa))) return e;
         if (need_phase) ca.phase_mode = PHASE_STORED;
     }
@@ -1327,14 +1347,10 @@ extern "C" int slmgs_run_accumulate(slmgs_ctx* c, const slmgs_params* p, float w
         else e = update_weights_pixel_impl(c, p);
         if (e) return e;
     }
-    ca.wgs_update = in_kernel ? 1 : 0;
-    ca.w_in_slot = c->w_pending;
-    if (ca.wgs_update) {
-        ca.w_out_slot = (c->w_pending == ACC_W0) ? ACC_W1 : ACC_W0;
-        if ((e = zero_slot(c, ca.w_out_slot))) return e;
-    }
+    ca.wgs_update = fused_update ? 1 : 0;
+    ca.w_in_slot = -1;
+    if (fused_update) ca.wsq_slot = ACC_TMP;
     if ((e = run_col(c, COL_FUSED, ca))) return e;
-    if (ca.wgs_update) c->w_pending = ca.w_out_slot;
     RowArgs rl = row_args(c);
     rl.mp_sum = (cf*)sum;
     rl.mp_weight = weight;

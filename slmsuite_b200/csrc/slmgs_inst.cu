@@ -38,6 +38,10 @@ int SLMGS_CAT(launch_row_, SLMGS_N)(int mode, int gx, int gy, int nthreads, rt_s
             return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
         }
         case ROW_LAST: {
+            if (a.colflag) {
+                typedef RowKernel<SLMGS_N, ROW_LAST, false, true> K;
+                return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
+            }
             typedef RowKernel<SLMGS_N, ROW_LAST> K;
             return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
         }

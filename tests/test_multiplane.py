@@ -71,3 +71,54 @@ def test_multiplane_api_and_errors(backend):
     assert g.shape == slm and g.dtype == np.uint8
     m.reset(reset_phase=False)
     assert m.iter == 0 and a.iter == 0 and a.amp_ff is None
+
+
+@pytest.mark.parametrize("method,kw", [("GS", {}), ("WGS-Leonardo", {}), ("WGS-Kim", {"fix_phase_iteration": 3})])
+def test_multiplane_fused_update_sparse_equals_dense_and_oracle(method, kw, backend, monkeypatch):
+    """The fused child iteration (slmgs_run_accumulate) with the in-kernel update (sum(w_new^2) pre-pass, immediate
+    normalisation) and the sparse far field: spot targets on wide far fields, against the dense loop and the oracle."""
+    from oracle import gs_oracle
+    from slmsuite_b200 import Hologram, MultiplaneHologram
+
+    monkeypatch.setenv("SLMGS_COL_THREADS", "32")  # four-column tiles on both backends
+    rng = np.random.default_rng(31)
+    slm = (40, 100)
+    amp = np.exp(-np.linspace(-1, 1, slm[1]) ** 2)[None, :] * np.ones(slm)
+    ph = rng.uniform(-np.pi, np.pi, slm).astype(np.float32)
+    yy, xx = np.mgrid[-1:1:slm[0] * 1j, -1:1:slm[1] * 1j]
+
+    def spots(shape, cols, seed):
+        r = np.random.default_rng(seed)
+        t = np.zeros(shape, dtype=np.float32)
+        for c in cols:
+            t[r.integers(0, shape[0], 2), c] = r.uniform(0.5, 1.5, 2)
+        return t
+
+    def build(H, M):
+        a = H(spots((64, 256), [5, 100, 101], 1), amp=amp.astype(np.float32), phase=ph, slm_shape=slm)
+        b = H(spots((128, 256), [30, 200], 2), amp=amp.astype(np.float32), phase=ph, slm_shape=slm,
+              propagation_kernel=(2.5 * (xx * xx + yy * yy)).astype(np.float32))
+        return M([a, b], weights=[1.0, 0.7])
+
+    res = []
+    for sparse in (True, False):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = build(Hologram, MultiplaneHologram)
+            for h in m.holograms:
+                h.set_sparse(sparse)
+            m.optimize(method, maxiter=7, verbose=False, **kw)
+        res.append(m)
+    a, b = res
+    assert all(h.sparse_info()[0] for h in a.holograms) and not any(h.sparse_info()[0] for h in b.holograms)
+    dphi = np.angle(np.exp(1j * (a.phase.astype(np.float64) - b.phase.astype(np.float64))))
+    assert np.sqrt(np.mean(dphi ** 2)) <= 2e-5
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o = build(gs_oracle.OracleHologram, gs_oracle.OracleMultiplaneHologram)
+        o.optimize(method, maxiter=7, verbose=False, **kw)
+    dphi = np.angle(np.exp(1j * (a.phase.astype(np.float64) - o.phase.astype(np.float64))))
+    assert np.sqrt(np.mean(dphi ** 2)) <= 2e-5
+    for ha, ho in zip(a.holograms, o.holograms):
+        assert rel_rmse(ha.amp_ff, ho.amp_ff) <= 1e-5
+        assert rel_rmse(ha.weights, ho.weights) <= 1e-5

@@ -191,3 +191,32 @@ def test_random_compressed_case_matches_oracle(seed, backend):
     nf = np.abs(b.nearfield)
     ok = nf > 1e-4 * nf.max()
     assert np.sqrt(np.mean(dphi[ok] ** 2)) <= 1e-4, info
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_consecutive_optimize_calls_match_oracle(seed, backend):
+    """optimize() called twice (second call starts with iter > 0, i.e. with a weight update in its first iteration and
+    whatever normalisation the first call left pending), with a method switch in between."""
+    from slmsuite_b200 import Hologram
+
+    c = make_case(100 + seed)
+    if c["kind"] == "dense":
+        c["target"] = np.where(np.random.default_rng(seed).random(c["target"].shape) < 0.02, c["target"], 0).astype(np.float32)
+        c["target"][0, 0] = 1.0
+    second = METHODS[(METHODS.index(c["method"]) + 1 + seed) % len(METHODS)]
+    args = dict(phase=c["phase"], slm_shape=c["slm"], propagation_kernel=c["prop"])
+    out = []
+    for cls in (Hologram, gs_oracle.OracleHologram):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            h = cls(c["target"], amp=None if c["amp"] is None else c["amp"].copy(), **args)
+            h.optimize(c["method"], maxiter=2, verbose=False, **c["kw"])
+            kw2 = {"fix_phase_iteration": 2} if second == "WGS-Kim" else {}
+            h.optimize(second, maxiter=3, verbose=False, **kw2)
+        out.append(h)
+    a, b = out
+    info = (seed, c["target"].shape, c["slm"], c["method"], second, c["kind"], a.sparse_info())
+    assert int(a.iter) == int(b.iter) == 5
+    assert rel_rmse(a.amp_ff, b.amp_ff) <= 1e-5, info
+    assert rel_rmse(a.weights, b.weights) <= 1e-5, info
+    assert bool(a.flags.get("fixed_phase", False)) == bool(b.flags.get("fixed_phase", False)), info

@@ -105,3 +105,25 @@ def test_pixel_sharded_compressed_hologram_gloo(world, emu):
         assert rel(farfield, ref.farfield) <= 1e-4
         # every rank holds the same full phase
         assert np.array_equal(phase, results[0][0])
+
+
+@pytest.mark.gpu
+def test_pixel_sharded_compressed_hologram_nccl(cuda):
+    """The same over NCCL on two GPUs (skipped on a single-GPU box): tools/sharded_compressed_demo.py asserts the
+    sharded result against the single-GPU hologram."""
+    import subprocess
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port),
+                          os.path.join(ROOT, "tools", "sharded_compressed_demo.py"), "200"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "speed-up" in out.stdout

@@ -168,3 +168,43 @@ def test_errors(backend):
         h.optimize("WGS-Leonardo", maxiter=2, verbose=False, feedback="experimental_spot")
     with pytest.raises(ValueError):
         h.optimize("nope", maxiter=1, verbose=False)
+
+
+def test_accepts_the_reference_cameraslm_object(emu):
+    """Drop-in check where the reference tree is present (build container only): the reference's own FourierSLM object
+    is passed as ``cameraslm=`` to both classes and the results agree."""
+    from oracle import ref_loader
+
+    if not ref_loader.reference_available():
+        pytest.skip("reference tree not present")
+    ref_loader.load_reference()
+    from slmsuite.hardware.cameras.simulated import SimulatedCamera
+    from slmsuite.hardware.cameraslms import FourierSLM
+    from slmsuite.hardware.slms.simulated import SimulatedSLM
+    from slmsuite.holography.algorithms import CompressedSpotHologram as RefCompressed
+
+    from slmsuite_b200 import CompressedSpotHologram
+
+    rng = np.random.default_rng(17)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        slm = SimulatedSLM((72, 56), pitch_um=(8, 8))
+        M = np.array([[4000.0, 150.0], [-120.0, 3800.0]])
+        b = np.array([[400.0], [300.0]])
+        cam = SimulatedCamera(slm, resolution=(800, 600), M=M, b=b, bitdepth=8)
+        fs = FourierSLM(cam, slm)
+        fs.calibrations["fourier"] = {"M": M, "b": b, "a": np.array([[0.0], [0.0]])}
+        v = np.vstack([rng.uniform(-0.02, 0.02, (2, 9)), rng.uniform(-2e-4, 2e-4, (1, 9))])
+        phase = rng.uniform(-np.pi, np.pi, slm.shape).astype(np.float32)
+        ref = RefCompressed(v.copy(), basis="kxy", cameraslm=fs)
+        ref.reset_phase(phase)
+        ref.reset(reset_phase=False)
+        ref.optimize("WGS-Leonardo", maxiter=5, verbose=False)
+        mine = CompressedSpotHologram(v.copy(), basis="kxy", cameraslm=fs, phase=phase)
+        mine.optimize("WGS-Leonardo", maxiter=5, verbose=False)
+    assert np.abs(mine.spot_zernike - ref.spot_zernike).max() < 1e-9
+    assert np.array_equal(mine.zernike_basis, ref.zernike_basis)
+    assert tuple(mine.shape) == tuple(int(s) for s in ref.shape)
+    assert rel(mine.amp_ff, ref.amp_ff) <= 1e-5
+    assert rel(mine.weights, ref.weights) <= 1e-5
+    assert phase_rms(mine.phase, ref.phase) <= 1e-4

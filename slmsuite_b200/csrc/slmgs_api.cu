@@ -5,6 +5,9 @@
 #include "slmgs_dispatch.h"
 #include "slmgs_pointwise.h"
 
+#ifndef SLMGS_EMULATE
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked)
+#endif
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -79,6 +82,12 @@ static LaunchInfo size_info(int n) {
 }
 static int launch_row(int n, int mode, int gx, int gy, int nt, rt_stream s, const RowArgs& a) {
 #define X(N_) if (n == N_) return launch_row_##N_(mode, gx, gy, nt, s, a);
+    SLMGS_FOR_SIZES(X)
+#undef X
+    return -1;
+}
+static int launch_colp(int n, int var, int dense, int gx, int gy, int nt, rt_stream s, const ColArgs& a) {
+#define X(N_) if (n == N_) return launch_colp_##N_(var, dense, gx, gy, nt, s, a);
     SLMGS_FOR_SIZES(X)
 #undef X
     return -1;
@@ -163,6 +172,13 @@ struct slmgs_ctx {
     bool profiling;
     bool use_pdl;
     bool prefetch;
+    bool pairs;                // fld is stored row-pair interleaved (slmgs_kernels.h, RowArgs)
+    // persistent fused column kernel with TMA-staged tiles (ColKernelP)
+    bool colp;                 // used for COL_FUSED launches of this context
+    bool colp_dense;           // slm rows == padded rows
+    void* tmap_dev;            // device copy of the CUtensorMap over fld
+    int n_boxes;               // boxes (groups of p_box_rows rows) holding SLM rows
+    signed char box_slot[32];  // their staging slots, -1 = box without SLM rows
 #ifndef SLMGS_EMULATE
     cudaEvent_t t0, t1;
     std::vector<cudaEvent_t> ev_pool;   // pairs
@@ -240,6 +256,29 @@ static int env_int(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
+// Persistent TMA column kernel: built for this column length, and every box of rows that holds SLM rows fits its
+// staging buffer (dense fields keep the boxes that do not fit as direct loads).  Fills box_slot / n_boxes.
+static bool colp_possible(slmgs_ctx* c) {
+    const LaunchInfo& li = c->icol;
+    if (li.p_npre <= 0 || env_int("SLMGS_TMA", 0) == 0 || c->pairs) return false;
+    if (li.p_ct > c->W) return false;
+    const int nbox = c->H / li.p_box_rows;
+    if (nbox > 32) return false;
+    c->colp_dense = c->h == c->H;
+    c->n_boxes = 0;
+    for (int m = 0; m < nbox; ++m) {
+        bool any = false;
+        for (int r = 0; r < li.p_box_rows && !any; ++r) {
+            const int n = m * li.p_box_rows + r;
+            const int sr = ((n + c->H / 2) & (c->H - 1)) - c->i0;
+            any = sr >= 0 && sr < c->h;
+        }
+        c->box_slot[m] = any ? (signed char)c->n_boxes++ : (signed char)-1;
+    }
+    for (int m = nbox; m < 32; ++m) c->box_slot[m] = -1;
+    return c->colp_dense || c->n_boxes <= li.p_npre;
+}
+
 static void choose_geometry(slmgs_ctx* c) {
     const int want = 2 * c->sms;  // at least two waves of blocks when the problem allows
     // rows: lines per block L = threads / tpl
@@ -261,6 +300,10 @@ static void choose_geometry(slmgs_ctx* c) {
         c->row_threads = nt;
         const int lines = nt / li.tpl;
         c->row_gx = (c->h + lines - 1) / lines;
+        // row-pair interleaved field layout: two lines per warp in the row kernels, so an even number of lines per
+        // block; not built for 8192-point rows (one line per block)
+        // (H >= 32: the column kernel steps through rows b + (H/R0) m and relies on an even H/R0)
+        c->pairs = env_int("SLMGS_PAIRS", 1) != 0 && c->W < 8192 && lines % 2 == 0 && c->H >= 32;
     }
     // columns: C = threads / tpl columns per block; keep >= 4 columns (one 32-byte sector per row)
     {
@@ -278,15 +321,54 @@ static void choose_geometry(slmgs_ctx* c) {
         // zero-padded problems (SLM rows <= half the padded rows) move little field data per tile: two
         // half-width blocks per SM overlap better than one full-width block (+7.6 % on the bench workload),
         // while dense problems need the full 32-byte row segments (-8 % with half-width tiles)
-        if (nt == li.maxt && 2 * c->h <= c->H && li.maxt / li.tpl >= 4 && li.maxt >= 1024) nt = li.maxt / 2;
+        // With the row-pair interleaved field layout a half-width tile still reads whole sectors (2 rows x 2 columns), so
+        // the two-blocks-per-SM geometry also wins on dense fields (+4 % on dense 4096^2 GS, B200).
+        if (nt == li.maxt && (2 * c->h <= c->H || c->pairs) && li.maxt / li.tpl >= 4 && li.maxt >= 1024 && !colp_possible(c))
+            nt = li.maxt / 2;
         int o = env_int("SLMGS_COL_THREADS", 0);
         if (o >= li.tpl && o >= 32 && o <= li.maxt && (o & (o - 1)) == 0 && o / li.tpl <= c->W) nt = o;
         c->col_threads = nt;
         c->col_gx = c->W / (nt / li.tpl);
+        c->colp = nt == li.maxt && colp_possible(c);
     }
 }
 
+#ifndef SLMGS_EMULATE
+typedef CUresult (*slmgs_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+#endif
+// tensor map over fld for the persistent column kernel: dims {W, H, B} of 8-byte elements, box {C, box rows, 1}
+static int make_tensor_map(slmgs_ctx* c) {
+#ifndef SLMGS_EMULATE
+    slmgs_encode_fn encode = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&encode, cudaEnableDefault, &qres) != cudaSuccess || !encode) {
+        cudaGetLastError();
+        return 1;
+    }
+    CUtensorMap tm;
+    cuuint64_t dims[3] = {(cuuint64_t)c->W, (cuuint64_t)c->H, (cuuint64_t)c->B};
+    cuuint64_t strides[2] = {(cuuint64_t)c->W * sizeof(cf), (cuuint64_t)c->W * c->H * sizeof(cf)};
+    cuuint32_t box[3] = {(cuuint32_t)c->icol.p_ct, (cuuint32_t)c->icol.p_box_rows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    if (encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, c->fld, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 1;
+    if (cudaMalloc(&c->tmap_dev, sizeof tm) != cudaSuccess) {
+        cudaGetLastError();
+        c->tmap_dev = nullptr;
+        return 1;
+    }
+    if (cudaMemcpy(c->tmap_dev, &tm, sizeof tm, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
+#else
+    (void)c;
+#endif
+    return 0;
+}
+
 extern "C" int slmgs_version(void) { return 100; }
+
 
 extern "C" const char* slmgs_last_error(const slmgs_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 
@@ -339,6 +421,10 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
     c->last_sparse = false;
     c->sref = nullptr;
     c->profiling = false;
+    c->colp = false;
+    c->colp_dense = false;
+    c->tmap_dev = nullptr;
+    c->n_boxes = 0;
     c->use_pdl = env_int("SLMGS_PDL", 1) != 0;
     // L2 prefetch of the next tile's field rows: +2.4 % on dense 4096^2, -0.4 % on zero-padded problems
     c->prefetch = env_int("SLMGS_PREFETCH", (h == H) ? 1 : 0) != 0;
@@ -389,6 +475,7 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
         CR(rt_check(c, rt_h2d(c->twA_col, a.data(), a.size() * sizeof(cf), c->stream), "twiddle upload"));
         CR(rt_check(c, rt_h2d(c->twB_col, b.data(), b.size() * sizeof(cf), c->stream), "twiddle upload"));
     }
+    if (c->colp && make_tensor_map(c)) c->colp = false;  // no TMA descriptor: the plain column kernel takes over
     CR(rt_check(c, rt_sync(c->stream), "sync"));
 #undef CR
     *out = c;
@@ -402,7 +489,8 @@ extern "C" int slmgs_destroy(slmgs_ctx* c) {
     void* ptrs[] = {c->fld, c->farfield, c->stage_c, c->stage_f, c->phase, c->amp, c->prop, c->target,
                     c->weights, c->phase_ff, c->amp_ff, c->twA_row, c->twB_row, c->twA_col, c->twB_col, c->acc,
                     c->partial, c->spot_x, c->spot_y, c->spot_amp, c->spot_pw, c->phase_saved, c->mp_sum, c->zero_w,
-                    c->tile_flags, c->tile_list, c->tile_byte, c->tile_count, c->samp_y, c->samp_x, c->scratch, c->winf};
+                    c->tile_flags, c->tile_list, c->tile_byte, c->tile_count, c->samp_y, c->samp_x, c->scratch, c->winf,
+                    c->tmap_dev};
     for (void* p : ptrs)
         if (p) rt_free(p);
 #ifndef SLMGS_EMULATE
@@ -674,6 +762,7 @@ static RowArgs row_args(slmgs_ctx* c) {
     a.zero_bs = ACC_N;
     a.pdl = (c->use_pdl && !c->profiling) ? 1 : 0;
     a.pf_dist = c->prefetch ? c->sms * (c->row_threads <= 512 ? 2 : 1) : 0;
+    a.pairs = c->pairs ? 1 : 0;
     if (c->sparse_now) {
         a.colflag = c->tile_byte;
         a.colflag_bs = c->W / (c->col_threads / c->icol.tpl);
@@ -720,6 +809,10 @@ static ColArgs col_args(slmgs_ctx* c) {
         a.tile_count = c->tile_count;
         a.tiles_bs = c->W / (c->col_threads / c->icol.tpl);
     }
+    a.pairs = c->pairs ? 1 : 0;
+    a.tmap = c->tmap_dev;
+    a.n_boxes = c->n_boxes;
+    memcpy(a.box_slot, c->box_slot, sizeof a.box_slot);
     return a;
 }
 // profiling: bracket a launch with events from a pool (class k: 0..2 row modes, 3..5 column modes)
@@ -756,7 +849,17 @@ static int run_col(slmgs_ctx* c, int mode, const ColArgs& a) {
         else if (a.wgs_update && pow_like && a.phase_mode == PHASE_STORED) var = VAR_POW_STORED;
     }
     const int gx = a.tiles ? c->n_active : c->col_gx;
-    int e = rt_check(c, launch_col(c->H, mode, var, gx, c->B, c->col_threads, c->stream, a), "column kernel launch");
+    int e;
+    if (mode == COL_FUSED && c->colp) {
+        // persistent: about one block per SM over the whole batch, each walking over its share of the tiles
+        int pgx = c->sms / c->B;
+        if (pgx < 1) pgx = 1;
+        if (pgx > gx) pgx = gx;
+        e = rt_check(c, launch_colp(c->H, var, c->colp_dense ? 1 : 0, pgx, c->B, c->col_threads, c->stream, a),
+                     "persistent column kernel launch");
+    } else {
+        e = rt_check(c, launch_col(c->H, mode, var, gx, c->B, c->col_threads, c->stream, a), "column kernel launch");
+    }
     prof_mark(c, 3 + mode, false);
     return e;
 }

@@ -73,6 +73,45 @@ inline void cp_async_wait_all() {}
 inline float ld_cached(const float* p) { return *p; }
 #endif
 
+// ---------------------------------------------------------------------------------------
+// TMA (cp.async.bulk.tensor) + mbarrier: asynchronous staging of field tiles in shared memory.
+// Under emulation the copy is done synchronously by the issuing thread (phases run one after the
+// other, so the data is there when the consumers' phase starts) and the barrier is a no-op.
+// ---------------------------------------------------------------------------------------
+#if defined(__CUDACC__) && !defined(SLMGS_EMULATE)
+SLMGS_DEVICE unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+SLMGS_DEVICE void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+SLMGS_DEVICE void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+SLMGS_DEVICE void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+// box {C columns, 256 rows, 1 hologram} of the row-major field at (x, y, z) -> dense [256][C] block in shared memory
+SLMGS_DEVICE void tma_load_box(void* smem_dst, const void* tmap, int x, int y, int z, unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+        : "memory");
+}
+SLMGS_DEVICE void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+#else
+inline void mbar_init(unsigned long long*, int) {}
+inline void mbar_expect_tx(unsigned long long*, unsigned) {}
+inline void mbar_wait(unsigned long long*, unsigned) {}
+inline void fence_proxy_async() {}
+#endif
+
 // log2 of a power of two
 #if defined(__CUDACC__) && !defined(SLMGS_EMULATE)
 SLMGS_DEVICE int ilog2(int x) { return __ffs(x) - 1; }
@@ -82,17 +121,33 @@ inline int ilog2(int x) { return __builtin_ctz((unsigned)x); }
 
 SLMGS_HD cf cmake(float re, float im) { return make_float2(re, im); }
 #if defined(__CUDA_ARCH__) && !defined(SLMGS_EMULATE) && defined(SLMGS_PACKED_F32X2)
-// Blackwell packed FP32x2 (FADD2 / FFMA2): one issue slot per complex add / subtract
+// Blackwell packed FP32x2 (FADD2 / FMUL2 / FFMA2): one issue slot per complex add / subtract, two per complex
+// multiply.  ptxas folds the operand shapes used below into the instruction's own modifiers -- a scalar broadcast
+// (`R.F32`) and a swapped pair with one half negated (`R.F32x2.LO_HI.NP`) -- so no MOV is spent on them:
+//     a * w       = (a.x, a.y) * w.x + (-a.y,  a.x) * w.y        FMUL2 + FFMA2
+//     a * conj(w) = (a.x, a.y) * w.x + ( a.y, -a.x) * w.y        FMUL2 + FFMA2
+// Rounding is that of the scalar FMUL + FFMA sequence the compiler contracts the plain expression to.
 SLMGS_HD cf cadd(cf a, cf b) { return __fadd2_rn(a, b); }
 SLMGS_HD cf csub(cf a, cf b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
+SLMGS_HD cf cmul(cf a, cf b) {
+    return __ffma2_rn(make_float2(-a.y, a.x), make_float2(b.y, b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
+}
+// a * conj(b)
+SLMGS_HD cf cmulc(cf a, cf b) {
+    return __ffma2_rn(make_float2(a.y, -a.x), make_float2(b.y, b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
+}
+SLMGS_HD cf cscale(cf a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+// a + s * b, a - i s b ... helpers for the constant twiddles of the in-register butterflies
+SLMGS_HD cf caxpy(float s, cf b, cf a) { return __ffma2_rn(b, make_float2(s, s), a); }
 #else
 SLMGS_HD cf cadd(cf a, cf b) { return make_float2(a.x + b.x, a.y + b.y); }
 SLMGS_HD cf csub(cf a, cf b) { return make_float2(a.x - b.x, a.y - b.y); }
-#endif
 SLMGS_HD cf cmul(cf a, cf b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 // a * conj(b)
 SLMGS_HD cf cmulc(cf a, cf b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
 SLMGS_HD cf cscale(cf a, float s) { return make_float2(a.x * s, a.y * s); }
+SLMGS_HD cf caxpy(float s, cf b, cf a) { return make_float2(a.x + s * b.x, a.y + s * b.y); }
+#endif
 // a * w (DIR=+1) or a * conj(w) (DIR=-1)
 template <int DIR> SLMGS_HD cf cmul_dir(cf a, cf w) { return DIR > 0 ? cmul(a, w) : cmulc(a, w); }
 // multiply by -i (DIR=+1, forward) or +i (DIR=-1, inverse)
@@ -126,13 +181,14 @@ template <int DIR, int R, int E> SLMGS_HD cf ctwiddle_const(cf v) {
     constexpr float c = root32_cos(k);
     constexpr float s = DIR > 0 ? -root32_sin(k) : root32_sin(k);
     if (k == 4 || k == 12 || k == 20 || k == 28) {
-        // |c| == |s| == sqrt(1/2): two adds + two multiplies
+        // |c| == |s| == sqrt(1/2):  (x + i y)(sc + i ss) q = ((x, y) + (ss/sc) (-y, x)) * (sc q): one packed add with a
+        // swapped operand + one packed multiply by a scalar
         constexpr float q = 0.70710678118654757f;
         constexpr float sc = c > 0 ? 1.0f : -1.0f, ss = s > 0 ? 1.0f : -1.0f;
-        // (x + i y)(c + i s) = (x c - y s) + i (x s + y c)
-        return make_float2((sc * v.x - ss * v.y) * q, (ss * v.x + sc * v.y) * q);
+        return cscale(caxpy(ss * sc, make_float2(-v.y, v.x), v), sc * q);
     }
-    return make_float2(v.x * c - v.y * s, v.x * s + v.y * c);
+    // (x + i y)(c + i s) = (x, y) c + (-y, x) s
+    return caxpy(s, make_float2(-v.y, v.x), cscale(v, c));
 }
 
 // ---------------------------------------------------------------------------------------

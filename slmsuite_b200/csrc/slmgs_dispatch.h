@@ -17,11 +17,15 @@ struct LaunchInfo {
     int padn;    // padded line length (complex elements)
     int ns;      // number of radix stages
     int r0, r1, r2;  // stage radices of the plan (twiddle table layout)
+    int p_npre;      // persistent TMA column kernel (ColKernelP): staged boxes per tile, 0 = not built for this size
+    int p_ct;        // ... its tile width (columns) at maxt threads
+    int p_box_rows;  // ... rows per box
 };
 
 #define SLMGS_DECL(N_)                                                                                        \
     int launch_row_##N_(int mode, int gx, int gy, int nthreads, rt_stream s, const RowArgs& a);               \
     int launch_col_##N_(int mode, int var, int gx, int gy, int nthreads, rt_stream s, const ColArgs& a);               \
+    int launch_colp_##N_(int var, int dense, int gx, int gy, int nthreads, rt_stream s, const ColArgs& a);             \
     LaunchInfo launch_info_##N_();
 SLMGS_DECL(16)
 SLMGS_DECL(32)

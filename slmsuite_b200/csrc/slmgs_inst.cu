@@ -11,42 +11,55 @@
 
 namespace slmgs {
 
-int SLMGS_CAT(launch_row_, SLMGS_N)(int mode, int gx, int gy, int nthreads, rt_stream s, const RowArgs& a) {
+template <int LI> static int launch_row_li(int mode, int gx, int gy, int nthreads, rt_stream s, const RowArgs& a) {
     switch (mode) {
         case ROW_FIRST: {
             if (a.colflag) {
-                typedef RowKernel<SLMGS_N, ROW_FIRST, false, true> K;
+                typedef RowKernel<SLMGS_N, ROW_FIRST, false, true, LI> K;
                 return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
             }
-            typedef RowKernel<SLMGS_N, ROW_FIRST> K;
+            typedef RowKernel<SLMGS_N, ROW_FIRST, false, false, LI> K;
             return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
         }
         case ROW_FUSED: {
             if (a.colflag) {  // sparse far field: only the column tiles the column kernel processes are moved
                 if (a.store_phase) {
-                    typedef RowKernel<SLMGS_N, ROW_FUSED, true, true> K;
+                    typedef RowKernel<SLMGS_N, ROW_FUSED, true, true, LI> K;
                     return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
                 }
-                typedef RowKernel<SLMGS_N, ROW_FUSED, false, true> K;
+                typedef RowKernel<SLMGS_N, ROW_FUSED, false, true, LI> K;
                 return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
             }
             if (a.store_phase) {
-                typedef RowKernel<SLMGS_N, ROW_FUSED, true> K;
+                typedef RowKernel<SLMGS_N, ROW_FUSED, true, false, LI> K;
                 return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
             }
-            typedef RowKernel<SLMGS_N, ROW_FUSED, false> K;
+            typedef RowKernel<SLMGS_N, ROW_FUSED, false, false, LI> K;
             return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
         }
         case ROW_LAST: {
             if (a.colflag) {
-                typedef RowKernel<SLMGS_N, ROW_LAST, false, true> K;
+                typedef RowKernel<SLMGS_N, ROW_LAST, false, true, LI> K;
                 return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
             }
-            typedef RowKernel<SLMGS_N, ROW_LAST> K;
+            typedef RowKernel<SLMGS_N, ROW_LAST, false, false, LI> K;
             return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
         }
     }
     return -1;
+}
+
+// the row-pair interleaved field layout needs an even number of lines per block (two lines share every warp)
+int SLMGS_CAT(launch_row_, SLMGS_N)(int mode, int gx, int gy, int nthreads, rt_stream s, const RowArgs& a) {
+#if SLMGS_N < 8192
+    if (a.pairs) {
+        if ((nthreads / Fft<SLMGS_N>::TPL) % 2 != 0) return -1;
+        return launch_row_li<2>(mode, gx, gy, nthreads, s, a);
+    }
+#else
+    if (a.pairs) return -1;
+#endif
+    return launch_row_li<1>(mode, gx, gy, nthreads, s, a);
 }
 
 // a block of MAXT threads has a compile-time tile width (CT); smaller blocks derive it from blockDim
@@ -88,6 +101,32 @@ int SLMGS_CAT(launch_col_, SLMGS_N)(int mode, int var, int gx, int gy, int nthre
     return -1;
 }
 
+// persistent fused column kernel with TMA-staged tiles: long columns only, full-size blocks
+#if SLMGS_N >= 2048
+#define SLMGS_HAVE_COLP 1
+template <int VAR> static int launch_colp_var(int dense, int gx, int gy, int nthreads, rt_stream s, const ColArgs& a) {
+    typedef Fft<SLMGS_N> F;
+    constexpr int MAXT = 16384 / F::E;
+    if (nthreads != MAXT) return -1;
+    if (dense) {
+        typedef ColKernelP<SLMGS_N, VAR, MAXT / F::TPL, true> K;
+        return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
+    }
+    typedef ColKernelP<SLMGS_N, VAR, MAXT / F::TPL, false> K;
+    return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
+}
+int SLMGS_CAT(launch_colp_, SLMGS_N)(int var, int dense, int gx, int gy, int nthreads, rt_stream s, const ColArgs& a) {
+    switch (var) {
+        case VAR_GS: return launch_colp_var<VAR_GS>(dense, gx, gy, nthreads, s, a);
+        case VAR_POW: return launch_colp_var<VAR_POW>(dense, gx, gy, nthreads, s, a);
+        case VAR_POW_STORED: return launch_colp_var<VAR_POW_STORED>(dense, gx, gy, nthreads, s, a);
+        default: return launch_colp_var<VAR_GENERAL>(dense, gx, gy, nthreads, s, a);
+    }
+}
+#else
+int SLMGS_CAT(launch_colp_, SLMGS_N)(int, int, int, int, int, rt_stream, const ColArgs&) { return -1; }
+#endif
+
 LaunchInfo SLMGS_CAT(launch_info_, SLMGS_N)() {
     typedef Fft<SLMGS_N> F;
     LaunchInfo i;
@@ -99,7 +138,29 @@ LaunchInfo SLMGS_CAT(launch_info_, SLMGS_N)() {
     i.r0 = F::R0;
     i.r1 = F::R1;
     i.r2 = F::R2;
+    i.p_npre = 0;
+    i.p_ct = 0;
+    i.p_box_rows = 0;
+#ifdef SLMGS_HAVE_COLP
+    {
+        typedef ColKernelP<SLMGS_N, VAR_GS, (16384 / F::E) / F::TPL, true> K;
+        i.p_npre = K::NPRE;
+        i.p_ct = (16384 / F::E) / F::TPL;
+        i.p_box_rows = K::BOX_ROWS;
+    }
+#endif
     return i;
 }
 
 }  // namespace slmgs
+
+#if defined(SLMGS_TRACE) && !defined(SLMGS_EMULATE)
+// diagnostic build only (one size compiled with -DSLMGS_TRACE): switch the per-phase clock stamps on / off, read them
+extern "C" __attribute__((visibility("default"))) int slmgs_trace_enable(int on) {
+    return (int)cudaMemcpyToSymbol(slmgs::slmgs_trace_on, &on, sizeof on);
+}
+extern "C" __attribute__((visibility("default"))) int slmgs_trace_read(long long* out) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, slmgs::slmgs_trace_buf, sizeof(long long) * 8 * 2 * 64);
+}
+#endif

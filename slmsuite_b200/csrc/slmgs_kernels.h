@@ -178,8 +178,15 @@ SLMGS_HD float wgs_apply(float w, float fc) {
 // ==========================================================================================
 // Row kernel
 // ==========================================================================================
+// Layout of the working field `fld` (private to the row / column kernels):
+//   pairs == 0: row-major [H][W];
+//   pairs == 1: ROW-PAIR INTERLEAVED [H/2][W][2]: element (r, c) at ((r >> 1) W + c) 2 + (r & 1).  A 32-byte sector
+//               then holds 2 rows x 2 columns and a 64-byte segment 2 rows x 4 columns, so the column kernel's
+//               strided tile access touches half as many lines per request (or serves half-width tiles, two blocks
+//               per SM, with fully used sectors), while a row block that interleaves two lines in every warp
+//               (RowKernel<.., LI = 2>) still reads and writes contiguous 256-byte runs.
 struct RowArgs {
-    cf* fld;             // [B][H][W], rolled index space
+    cf* fld;             // [B][H][W], rolled index space (layout: see above)
     long long fld_bs;    // batch stride (elements)
     float* phase;        // [B][h][w] near-field phase (natural SLM order)
     long long phase_bs;
@@ -211,12 +218,15 @@ struct RowArgs {
                                    // processed by the column kernel); columns of other tiles are identically zero after
                                    // the far-field constraint, so they are neither stored nor loaded.  nullptr = dense
     int ctile_shift;               // log2(columns per column tile)
+    int pairs;                     // fld layout (must match LI of the kernel: LI == 2 <=> pairs)
 };
 
 // STORE (ROW_FUSED only): this launch also writes the phase (last iteration of a fused run)
 // SPARSE (ROW_FIRST / ROW_FUSED): spectrum columns are filtered through a.colflag
-template <int N, int MODE, bool STORE = false, bool SPARSE = false> struct RowKernel {
+// LI: lines interleaved in a warp (thread -> line tid % LI): 1 = row-major fld, 2 = row-pair interleaved fld
+template <int N, int MODE, bool STORE = false, bool SPARSE = false, int LI = 1> struct RowKernel {
     typedef Fft<N> F;
+    static constexpr int TRACE_CLASS = 20 + MODE;  // diagnostic builds (-DSLMGS_TRACE)
     typedef RowArgs Args;
     static constexpr int E = F::E, NS = F::NS;
     static constexpr int MAXT = 16384 / E;
@@ -226,13 +236,14 @@ template <int N, int MODE, bool STORE = false, bool SPARSE = false> struct RowKe
     };
 
     static size_t smem_bytes(int nthreads) { return NS > 1 ? (size_t)(nthreads / F::TPL) * F::PADN * sizeof(cf) : 0; }
+    static constexpr int TEAM = LI * F::TPL;  // threads that exchange data: the LI interleaved lines of a warp set
 
 #ifndef SLMGS_EMULATE
-    // Lines are independent: only the TPL threads of one line exchange data, so they synchronise on their own
-    // named barrier (one per line) instead of the whole block when a line owns whole warps.
+    // Lines are independent: only the threads of one team exchange data, so they synchronise on their own
+    // named barrier (one per team) instead of the whole block when a team owns whole warps.
     static SLMGS_DEVICE void barrier(const ThreadId& id) {
-        if constexpr (F::TPL >= 128) {
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + id.tid / F::TPL), "n"(F::TPL) : "memory");
+        if constexpr (TEAM >= 128) {
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + id.tid / TEAM), "n"(TEAM) : "memory");
         } else {
             __syncthreads();
         }
@@ -248,14 +259,17 @@ template <int N, int MODE, bool STORE = false, bool SPARSE = false> struct RowKe
     };
     static SLMGS_DEVICE Loc locate(const Args& a, cf* smem, const ThreadId& id) {
         Loc L;
-        const int line = id.tid / F::TPL;
+        const int team = id.tid / TEAM;
+        const int line = team * LI + id.tid % LI;
         const int lines = id.nthreads / F::TPL;
-        L.lt = id.tid % F::TPL;
+        L.lt = (id.tid % TEAM) / LI;
         L.sr = id.bx * lines + line;
         L.active = L.sr < a.h;
         L.fr = (L.sr + a.i0 + (a.H >> 1)) & (a.H - 1);
-        L.s = smem + (size_t)line * F::PADN;
-        L.fbase = (long long)id.by * a.fld_bs + (long long)L.fr * a.W;
+        L.s = smem + (size_t)team * (F::PADN * LI) + id.tid % LI;
+        // element k of the row sits at fbase + k * LI
+        if (LI == 2) L.fbase = (long long)id.by * a.fld_bs + (long long)(L.fr >> 1) * a.W * 2 + (L.fr & 1);
+        else L.fbase = (long long)id.by * a.fld_bs + (long long)L.fr * a.W;
         L.pbase = (long long)id.by * a.phase_bs + (long long)L.sr * a.w;
         L.cbase = (long long)id.by * a.colflag_bs;
         return L;
@@ -299,7 +313,7 @@ template <int N, int MODE, bool STORE = false, bool SPARSE = false> struct RowKe
                 const int k = F::last_index(L.lt + F::TPL * u, m);
                 bool on = L.active;
                 if (SPARSE) on = on && flag_byte(fl, m);
-                st.v[u * R + m] = on ? ld_stream(a.fld + L.fbase + k) : cmake(0.f, 0.f);
+                st.v[u * R + m] = on ? ld_stream(a.fld + L.fbase + k * LI) : cmake(0.f, 0.f);
             }
         }
     }
@@ -314,7 +328,7 @@ template <int N, int MODE, bool STORE = false, bool SPARSE = false> struct RowKe
             for (int m = 0; m < R; ++m) {
                 const int k = F::last_index(L.lt + F::TPL * u, m);
                 if (SPARSE && !flag_byte(fl, m)) continue;
-                a.fld[L.fbase + k] = st.v[u * R + m];
+                a.fld[L.fbase + k * LI] = st.v[u * R + m];
             }
         }
     }
@@ -398,7 +412,7 @@ template <int N, int MODE, bool STORE = false, bool SPARSE = false> struct RowKe
             if (a.zero_acc2 && id.bx == 0 && id.tid == 0) a.zero_acc2[(long long)id.by * a.zero_bs] = 0.0;
             if (a.win_dst && id.bx == 0 && id.tid == 0)
                 a.win_dst[id.by] = (float)(1.0 / sqrt(a.win_src[(long long)id.by * a.zero_bs]));
-            if (MODE != ROW_FIRST && a.pf_dist > 0) {
+            if (MODE != ROW_FIRST && LI == 1 && a.pf_dist > 0) {
                 // pull the rows of the tile this SM will run next into L2 while this tile computes
                 const int lines = id.nthreads / F::TPL;
                 const int nsr = (id.bx + a.pf_dist) * lines + id.tid / F::TPL;
@@ -411,22 +425,22 @@ template <int N, int MODE, bool STORE = false, bool SPARSE = false> struct RowKe
         }
         if constexpr (MODE == ROW_FIRST) {
             if constexpr (P == 0) build_nearfield(st, a, id, L);
-            F::template fwd_stage<P>(st.v, L.lt, a.twA, a.twB, L.s, 1);
+            F::template fwd_stage<P>(st.v, L.lt, a.twA, a.twB, L.s, LI);
             if constexpr (P == NS - 1) store_spectrum(st, a, L);
         } else if constexpr (MODE == ROW_LAST) {
             if constexpr (P == 0) load_spectrum(st, a, L);
-            F::template inv_stage<NS - 1 - P>(st.v, L.lt, a.twA, a.twB, L.s, 1);
+            F::template inv_stage<NS - 1 - P>(st.v, L.lt, a.twA, a.twB, L.s, LI);
             if constexpr (P == NS - 1) project<false, true>(st, a, id, L);
         } else {
             if constexpr (P == 0) load_spectrum(st, a, L);
             if constexpr (P < NS - 1) {
-                F::template inv_stage<NS - 1 - P>(st.v, L.lt, a.twA, a.twB, L.s, 1);
+                F::template inv_stage<NS - 1 - P>(st.v, L.lt, a.twA, a.twB, L.s, LI);
             } else if constexpr (P == NS - 1) {
-                F::template inv_stage<0>(st.v, L.lt, a.twA, a.twB, L.s, 1);
+                F::template inv_stage<0>(st.v, L.lt, a.twA, a.twB, L.s, LI);
                 project<true, STORE>(st, a, id, L);
-                F::template fwd_stage<0>(st.v, L.lt, a.twA, a.twB, L.s, 1);
+                F::template fwd_stage<0>(st.v, L.lt, a.twA, a.twB, L.s, LI);
             } else {
-                F::template fwd_stage<P - (NS - 1)>(st.v, L.lt, a.twA, a.twB, L.s, 1);
+                F::template fwd_stage<P - (NS - 1)>(st.v, L.lt, a.twA, a.twB, L.s, LI);
             }
             if constexpr (P == NPHASE - 1) store_spectrum(st, a, L);
         }
@@ -488,12 +502,18 @@ struct ColArgs {
                           // non-zero are launched), or nullptr = every tile, in order.  [B][tiles_bs]
     const int* tile_count;  // [B] active tiles of each hologram: blocks with blockIdx.x >= count exit at once
     int tiles_bs;
+    // persistent column kernel (ColKernelP): TMA staging of the field tiles
+    int pairs;            // fld layout: 0 row-major, 1 row-pair interleaved (see RowArgs)
+    const void* tmap;     // device copy of the CUtensorMap over fld: dims {W, H, B}, box {C, N/R0 rows, 1}
+    int n_boxes;          // zero-padded field: boxes (groups of N/R0 rows) that hold SLM rows ...
+    signed char box_slot[32];  // ... and the staging slot of each box (-1 = no SLM row inside: reads as zero)
 };
 
 // CT: columns per tile known at compile time (block of MAXT threads), 0 = derived from blockDim at run time
 // (small problems).  With CT fixed, every shared-memory access is base register + immediate offset.
 template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
     typedef Fft<N> F;
+    static constexpr int TRACE_CLASS = 10 + MODE;  // diagnostic builds (-DSLMGS_TRACE)
     typedef ColArgs Args;
     static constexpr int E = F::E, NS = F::NS;
     static constexpr int MAXT = 16384 / E;
@@ -518,12 +538,14 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
         cf* s;
         long long fbase, ibase, tbase;
     };
-    static SLMGS_DEVICE Loc locate(const Args& a, cf* smem, const ThreadId& id) {
+    static SLMGS_DEVICE Loc locate(const Args& a, cf* smem, const ThreadId& id) { return locate_q(a, smem, id, id.bx); }
+    // q: position of the block's tile in the launch order (the block index, or further tiles of a persistent block)
+    static SLMGS_DEVICE Loc locate_q(const Args& a, cf* smem, const ThreadId& id, int q) {
         Loc L;
         L.C = CT > 0 ? CT : id.nthreads / F::TPL;  // a power of two
         L.col = id.tid & (L.C - 1);
         L.lt = id.tid >> ilog2(L.C);
-        const int tile = a.tiles ? __ldg(a.tiles + (long long)id.by * a.tiles_bs + id.bx) : id.bx;
+        const int tile = a.tiles ? __ldg(a.tiles + (long long)id.by * a.tiles_bs + q) : q;
         L.gc = tile * L.C + L.col;
         L.s = smem + L.col;
         L.fbase = (long long)id.by * a.fld_bs + L.gc;
@@ -531,6 +553,13 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
         L.ibase = (long long)id.by * a.img_bs + (long long)tile * a.H * L.C + L.col;
         L.tbase = (long long)id.by * a.target_bs + (long long)tile * a.H * L.C + L.col;
         return L;
+    }
+    // Offset of element (row b, this thread's column) of `fld`; rows b + (N/R0) m follow at a constant step of
+    // (N/R0) W elements in both layouts (N/R0 is even).
+    static SLMGS_DEVICE long long row_base(const Args& a, const Loc& L, int b) {
+        const long long hb = L.fbase - L.gc;  // hologram base
+        if (a.pairs) return hb + ((long long)(b >> 1) * a.W + L.gc) * 2 + (b & 1);
+        return hb + (long long)b * a.W + L.gc;
     }
     // Rows of `fld` that hold the SLM (rolled index n): ((n + H/2) mod H) - i0 in [0, h).  Row n of butterfly
     // b is b + (N/R0) m, so the row pointer advances by a constant and the test is one unsigned compare.
@@ -541,7 +570,7 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
         SLMGS_UNROLL
         for (int u = 0; u < E / R; ++u) {
             const int b = L.lt + F::TPL * u;
-            const cf* p = a.fld + L.fbase + (long long)b * a.W;
+            const cf* p = a.fld + row_base(a, L, b);
             const unsigned r0 = (unsigned)(b + (a.H >> 1) - a.i0);
             SLMGS_UNROLL
             for (int m = 0; m < R; ++m) {
@@ -558,7 +587,7 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
         SLMGS_UNROLL
         for (int u = 0; u < E / R; ++u) {
             const int b = L.lt + F::TPL * u;
-            cf* p = a.fld + L.fbase + (long long)b * a.W;
+            cf* p = a.fld + row_base(a, L, b);
             const unsigned r0 = (unsigned)(b + (a.H >> 1) - a.i0);
             SLMGS_UNROLL
             for (int m = 0; m < R; ++m) {
@@ -825,7 +854,7 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
         } else {
             if constexpr (P == 0) {
                 load_rows(st, a, L);
-                if (a.pf_dist > 0 && a.h == a.H && !a.tiles) {
+                if (a.pf_dist > 0 && a.h == a.H && !a.tiles && !a.pairs) {
                     // dense field: pull the rows of the tile group this SM will run next into L2 (a 128-byte line
                     // holds 16 columns = several tiles, so one tile of each line-sharing group issues the prefetch)
                     const int per_line = 16 / L.C > 0 ? 16 / L.C : 1;
@@ -854,6 +883,162 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
                 F::template inv_stage<2 * NS - 2 - P>(st.v, L.lt, a.twA, a.twB, L.s, L.C);
             }
             if constexpr (P == NPHASE - 1) store_rows(st, a, L);
+        }
+    }
+};
+
+// ==========================================================================================
+// Persistent fused column kernel with TMA-staged tiles
+// ==========================================================================================
+// Same arithmetic as ColKernel<N, COL_FUSED, VAR, CT>, different data movement.  One block per SM walks over
+// tiles q = blockIdx.x + it * gridDim.x.  The shared memory that the exchange buffer leaves free holds NPRE
+// "boxes" of the NEXT tile -- box m = rows [m N/R0, (m+1) N/R0) x CT columns, exactly the rows that form element m
+// of the first-stage butterflies -- fetched by TMA (cp.async.bulk.tensor, completion on an mbarrier) while the
+// current tile runs its six radix stages.  A thread then reads its first-stage elements from the staging buffer
+// (conflict-free LDS at immediate offsets) instead of issuing strided global loads and waiting for them:
+//   * no exposed DRAM latency at the head of a tile for the staged boxes (dense 4096^2: 11 of 16; the last five
+//     do not fit next to the 137 KB exchange buffer and stay direct loads, issued before the mbarrier wait);
+//   * an LSU request of the strided pattern costs one L1 wavefront per row (8 per warp) -- the staged LDS costs 2;
+//   * no row-range predicates or 64-bit address arithmetic for the staged elements.
+// Zero-padded fields (DENSE = false): rows outside the SLM are never written and stay zero in `fld`, so whole
+// boxes are fetched; boxes without any SLM row are not fetched at all and read as zero.  The host only selects
+// this kernel when all boxes that hold SLM rows fit the staging buffer.
+template <int N, int VAR, int CT, bool DENSE> struct ColKernelP : ColKernel<N, COL_FUSED, VAR, CT> {
+    typedef ColKernel<N, COL_FUSED, VAR, CT> Base;
+    typedef typename Base::F F;
+    static constexpr int TRACE_CLASS = 30;
+    typedef ColArgs Args;
+    typedef typename Base::State State;
+    typedef typename Base::Loc Loc;
+    static constexpr int E = F::E, NS = F::NS, R0 = F::R0;
+    static constexpr int MAXT = Base::MAXT;
+    static constexpr int NPHASE = Base::NPHASE;
+    static_assert(CT > 0 && NS == 3, "persistent column kernel: compile-time tile width, three radix stages");
+    static constexpr int BOX_ROWS = N / R0;
+    static constexpr int BOX_ELEMS = BOX_ROWS * CT;
+    static constexpr size_t BOX_BYTES = (size_t)BOX_ELEMS * sizeof(cf);
+    static constexpr size_t EXCH_BYTES = (((size_t)F::PADN * CT * sizeof(cf)) + 127) / 128 * 128;
+    static constexpr size_t SMEM_MAX = 227 * 1024;
+    static constexpr int NPRE_FIT = (int)((SMEM_MAX - 16 - EXCH_BYTES) / BOX_BYTES);
+    static constexpr int NPRE = NPRE_FIT < R0 ? NPRE_FIT : R0;
+    static_assert(NPRE >= 1, "no room for a staging box");
+    static_assert(R0 <= 32, "box_slot table");
+
+    static size_t smem_bytes(int) { return EXCH_BYTES + (size_t)NPRE * BOX_BYTES + 16; }
+    static SLMGS_DEVICE cf* stage_of(cf* smem) { return reinterpret_cast<cf*>(reinterpret_cast<char*>(smem) + EXCH_BYTES); }
+    static SLMGS_DEVICE unsigned long long* bar_of(cf* smem) {
+        return reinterpret_cast<unsigned long long*>(stage_of(smem) + (size_t)NPRE * BOX_ELEMS);
+    }
+
+    static SLMGS_DEVICE int tile_count(const Args& a, const ThreadId& id) {
+        return a.tiles ? __ldg(a.tile_count + id.by) : a.W / CT;
+    }
+    static SLMGS_DEVICE bool skip(const Args& a, const ThreadId& id) { return id.bx >= tile_count(a, id); }
+    static SLMGS_DEVICE int iterations(const Args& a, const ThreadId& id) {
+        return (tile_count(a, id) - id.bx + id.gx - 1) / id.gx;
+    }
+    static SLMGS_DEVICE void init(const Args&, cf* smem, const ThreadId& id) {
+        if (id.tid == 0) mbar_init(bar_of(smem), 1);
+    }
+
+    // one thread: fetch the staged boxes of tile position q into the staging buffer
+    static SLMGS_DEVICE void prefetch(const Args& a, cf* smem, const ThreadId& id, int q) {
+        const int tile = a.tiles ? __ldg(a.tiles + (long long)id.by * a.tiles_bs + q) : q;
+        cf* stage = stage_of(smem);
+#if defined(__CUDACC__) && !defined(SLMGS_EMULATE)
+        unsigned long long* bar = bar_of(smem);
+        if (DENSE) {
+            mbar_expect_tx(bar, (unsigned)(NPRE * BOX_BYTES));
+#pragma unroll 1
+            for (int m = 0; m < NPRE; ++m) tma_load_box(stage + (size_t)m * BOX_ELEMS, a.tmap, tile * CT, m * BOX_ROWS, id.by, bar);
+        } else {
+            mbar_expect_tx(bar, (unsigned)(a.n_boxes * BOX_BYTES));
+#pragma unroll 1
+            for (int m = 0; m < R0; ++m) {
+                const int sl = a.box_slot[m];
+                if (sl >= 0) tma_load_box(stage + (size_t)sl * BOX_ELEMS, a.tmap, tile * CT, m * BOX_ROWS, id.by, bar);
+            }
+        }
+#else
+        for (int m = 0; m < R0; ++m) {
+            const int sl = DENSE ? (m < NPRE ? m : -1) : a.box_slot[m];
+            if (sl < 0) continue;
+            for (int r = 0; r < BOX_ROWS; ++r)
+                for (int cc = 0; cc < CT; ++cc)
+                    stage[(size_t)sl * BOX_ELEMS + r * CT + cc] =
+                        a.fld[(long long)id.by * a.fld_bs + (long long)(m * BOX_ROWS + r) * a.W + tile * CT + cc];
+        }
+#endif
+    }
+
+    // first-stage elements: staged boxes from shared memory, the rest (dense fields only) straight from global memory
+    static SLMGS_DEVICE void load_direct(State& st, const Args& a, const Loc& L) {
+        if constexpr (DENSE && NPRE < R0) {
+            const long long step = (long long)BOX_ROWS * a.W;
+            SLMGS_UNROLL
+            for (int u = 0; u < E / R0; ++u) {
+                const cf* p = a.fld + L.fbase + (long long)(L.lt + F::TPL * u) * a.W + (long long)NPRE * step;
+                SLMGS_UNROLL
+                for (int m = NPRE; m < R0; ++m) {
+                    st.v[u * R0 + m] = ld_stream(p);
+                    p += step;
+                }
+            }
+        }
+    }
+    static SLMGS_DEVICE void load_staged(State& st, const Args& a, cf* smem, const ThreadId& id, const Loc& L) {
+        const cf* sp = stage_of(smem) + id.tid;  // (lt * CT + col) == tid
+        SLMGS_UNROLL
+        for (int u = 0; u < E / R0; ++u) {
+            SLMGS_UNROLL
+            for (int m = 0; m < R0; ++m) {
+                if (DENSE) {
+                    if (m < NPRE) st.v[u * R0 + m] = sp[(size_t)m * BOX_ELEMS + (size_t)u * F::TPL * CT];
+                } else {
+                    const int sl = a.box_slot[m];
+                    st.v[u * R0 + m] = sl >= 0 ? sp[(size_t)sl * BOX_ELEMS + (size_t)u * F::TPL * CT] : cmake(0.f, 0.f);
+                }
+            }
+        }
+    }
+    static SLMGS_DEVICE void store_rows_p(State& st, const Args& a, const Loc& L) {
+        if constexpr (DENSE) {
+            const long long step = (long long)BOX_ROWS * a.W;
+            SLMGS_UNROLL
+            for (int u = 0; u < E / R0; ++u) {
+                cf* p = a.fld + L.fbase + (long long)(L.lt + F::TPL * u) * a.W;
+                SLMGS_UNROLL
+                for (int m = 0; m < R0; ++m) {
+                    *p = st.v[u * R0 + m];
+                    p += step;
+                }
+            }
+        } else {
+            Base::store_rows(st, a, L);
+        }
+    }
+
+    template <int P> static SLMGS_DEVICE void phase(State& st, const Args& a, cf* smem, const ThreadId& id) {
+        const int q = id.bx + id.it * id.gx;
+        const Loc L = Base::locate_q(a, smem, id, q);
+        if constexpr (P == 0) {
+            if (id.it == 0 && id.tid == 0) prefetch(a, smem, id, q);  // the block's first tile: nobody fetched it yet
+            load_direct(st, a, L);
+            mbar_wait(bar_of(smem), (unsigned)(id.it & 1));
+            load_staged(st, a, smem, id, L);
+            F::template fwd_stage<0>(st.v, L.lt, a.twA, a.twB, L.s, L.C);
+        } else if constexpr (P == 1) {
+            // every thread has read the staging buffer (barrier behind phase 0): fetch the next tile into it
+            if (id.tid == 0 && id.it + 1 < iterations(a, id)) prefetch(a, smem, id, q + id.gx);
+            F::template fwd_stage<1>(st.v, L.lt, a.twA, a.twB, L.s, L.C);
+        } else if constexpr (P == NS - 1) {
+            Base::prefetch_images_head(a, L);
+            F::template fwd_stage<NS - 1>(st.v, L.lt, a.twA, a.twB, L.s, L.C);
+            Base::template constrain<false>(st, a, id, L);
+            F::template inv_stage<NS - 1>(st.v, L.lt, a.twA, a.twB, L.s, L.C);
+        } else {
+            F::template inv_stage<2 * NS - 2 - P>(st.v, L.lt, a.twA, a.twB, L.s, L.C);
+            if constexpr (P == NPHASE - 1) store_rows_p(st, a, L);
         }
     }
 };

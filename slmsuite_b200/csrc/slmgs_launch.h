@@ -26,6 +26,7 @@ struct ThreadId {
     int nthreads;  // blockDim.x
     int bx, by;    // blockIdx.x, blockIdx.y
     int gx;        // gridDim.x
+    int it;        // persistent kernels: tile iteration of this block (0 otherwise)
 };
 
 // ---- block-level sum into a global double accumulator ------------------------------------
@@ -57,13 +58,46 @@ template <class K, class = void> struct has_skip {
 template <class K> struct has_skip<K, decltype((void)&K::skip)> {
     static constexpr bool value = true;
 };
+// optional K::iterations(args, id): PERSISTENT kernel -- the block runs its phase sequence that many times
+// (id.it = 0, 1, ...), with a barrier between iterations; optional K::init(args, smem, id) runs once per thread
+// before the first iteration, followed by a barrier (mbarrier set-up).
+template <class K, class = void> struct has_iterations {
+    static constexpr bool value = false;
+};
+template <class K> struct has_iterations<K, decltype((void)&K::iterations)> {
+    static constexpr bool value = true;
+};
 
 #ifndef SLMGS_EMULATE
+#ifdef SLMGS_TRACE
+// Build-time diagnostic (-DSLMGS_TRACE, never in the product build): per-phase SM clock stamps of a few blocks.
+// slot layout: [block 0..7][thread group 0..1][64 stamps]; stamp 2P = phase P done, 2P+1 = barrier behind it passed.
+static __device__ long long slmgs_trace_buf[8 * 2 * 64];
+static __device__ int slmgs_trace_on;
+template <class K, class = void> struct trace_class {
+    static constexpr int value = 0;
+};
+template <class K> struct trace_class<K, decltype((void)K::TRACE_CLASS)> {
+    static constexpr int value = K::TRACE_CLASS;
+};
+template <class K> SLMGS_DEVICE void trace_stamp(const ThreadId& id, int slot) {
+    if (slmgs_trace_on == trace_class<K>::value && id.bx < 8 && id.by == 0 && (id.tid == 0 || id.tid == id.nthreads - 1) && slot < 64) {
+        long long t;
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+        slmgs_trace_buf[(id.bx * 2 + (id.tid != 0)) * 64 + slot] = t;
+    }
+}
+#define SLMGS_STAMP(id, slot) trace_stamp<K>(id, slot)
+#else
+#define SLMGS_STAMP(id, slot)
+#endif
 template <class K, int P>
 SLMGS_DEVICE void run_phases(typename K::State& st, const typename K::Args& a, cf* smem, const ThreadId& id) {
     K::template phase<P>(st, a, smem, id);
+    SLMGS_STAMP(id, 2 + id.it * 2 * K::NPHASE + 2 * P);
     if constexpr (P + 1 < K::NPHASE) {
         K::barrier(id);
+        SLMGS_STAMP(id, 2 + id.it * 2 * K::NPHASE + 2 * P + 1);
         run_phases<K, P + 1>(st, a, smem, id);
     }
 }
@@ -91,10 +125,24 @@ template <class K> __global__ void __launch_bounds__(K::MAXT, min_blocks<K>::val
     // flushed (wait).  Both are no-ops when the kernel is launched without the PDL attribute.
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    id.it = 0;
     if constexpr (has_skip<K>::value) {
         if (K::skip(a, id)) return;
     }
-    run_phases<K, 0>(st, a, smem, id);
+    SLMGS_STAMP(id, 0);
+    if constexpr (has_iterations<K>::value) {
+        const int nit = K::iterations(a, id);
+        K::init(a, smem, id);
+        K::barrier(id);
+        for (int it = 0; it < nit; ++it) {
+            id.it = it;
+            run_phases<K, 0>(st, a, smem, id);
+            K::barrier(id);
+            SLMGS_STAMP(id, 2 + it * 2 * K::NPHASE + 2 * K::NPHASE - 1);
+        }
+    } else {
+        run_phases<K, 0>(st, a, smem, id);
+    }
 }
 
 // returns cudaError_t as int
@@ -149,10 +197,19 @@ int launch_kernel(int gx, int gy, int nthreads, size_t smem_bytes, void* /*strea
             id.bx = bx;
             id.by = by;
             id.gx = gx;
+            id.it = 0;
             if constexpr (has_skip<K>::value) {
                 if (K::skip(a, id)) continue;
             }
-            emu_phases<K, 0>(st, a, smem.data(), id);
+            if constexpr (has_iterations<K>::value) {
+                const int nit = K::iterations(a, id);
+                for (int it = 0; it < nit; ++it) {
+                    id.it = it;
+                    emu_phases<K, 0>(st, a, smem.data(), id);
+                }
+            } else {
+                emu_phases<K, 0>(st, a, smem.data(), id);
+            }
         }
     return 0;
 }

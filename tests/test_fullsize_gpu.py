@@ -241,3 +241,128 @@ def test_camera_2048_vs_oracle(cuda):
     diff = img.astype(np.int64) - gold.astype(np.int64)
     near = np.abs(raw - np.rint(raw)) <= 1e-3 * np.maximum(raw, 1.0)
     assert np.all(np.abs(diff) <= 1) and not np.any((diff != 0) & ~near)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Full-size parity against the oracle on every BASELINE config.  Tolerance: north_star's 1e-5 rel-RMSE
+# of the far-field amplitude; phases 2e-5 rad rms (5e-5 after 30 iterations).  The oracle needs ~5 s per iteration at
+# 4096^2 and ~20 s at 8192^2 on one host core, so the iteration counts are small where the size is large.
+# ------------------------------------------------------------------------------------------------------------------
+def _phase_rms(a, b, mask=None):
+    d = np.angle(np.exp(1j * (np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64))))
+    if mask is not None:
+        d = d[mask]
+    return float(np.sqrt(np.mean(d ** 2)))
+
+
+@pytest.mark.parametrize("variant", ["dense", "delta"])
+def test_config1_512_gs_30_iterations_vs_oracle(cuda, variant):
+    """BASELINE configs[0] exactly as SURVEY.md 8d writes it: 512^2, default_rng(0), GS, 30 iterations; dense target and
+    the reference test's single-delta form (tests/holography/test_algorithms.py:51-84)."""
+    from oracle import gs_oracle
+    from slmsuite_b200 import Hologram
+
+    rng = np.random.default_rng(0)
+    if variant == "dense":
+        target = rng.random((512, 512), dtype=np.float32)
+    else:
+        target = np.zeros((512, 512), dtype=np.float32)
+        target[rng.integers(512), rng.integers(512)] = 1
+    phase = rng.uniform(-np.pi, np.pi, (512, 512)).astype(np.float32)
+    a = Hologram(target, phase=phase)
+    a.optimize("GS", maxiter=30, verbose=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        b = gs_oracle.OracleHologram(target, phase=phase)
+        b.optimize("GS", maxiter=30, verbose=False)
+    assert a.iter == b.iter == 30
+    assert rel_rmse(a.amp_ff, b.amp_ff) <= 1e-5
+    nf = np.abs(b.nearfield)
+    assert _phase_rms(a.phase, b.phase, nf > 1e-4 * nf.max()) <= 5e-5
+
+
+def test_dense_gs_4096_three_iterations_vs_oracle(cuda):
+    """The metric's configuration (shape == slm_shape == 4096^2, dense target, GS): 3 iterations against the oracle."""
+    from oracle import gs_oracle
+    from slmsuite_b200 import Hologram
+
+    rng = np.random.default_rng(11)
+    target = rng.random((4096, 4096), dtype=np.float32)
+    phase = rng.uniform(-np.pi, np.pi, (4096, 4096)).astype(np.float32)
+    a = Hologram(target, phase=phase)
+    a.optimize("GS", maxiter=3, verbose=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        b = gs_oracle.OracleHologram(target, phase=phase)
+        b.optimize("GS", maxiter=3, verbose=False)
+    assert rel_rmse(a.amp_ff, b.amp_ff) <= 1e-5
+    nf = np.abs(b.nearfield)
+    assert _phase_rms(a.phase, b.phase, nf > 1e-4 * nf.max()) <= 2e-5
+
+
+def test_config3_spot_hologram_4096_vs_oracle(cuda):
+    """BASELINE configs[2]: SpotHologram 32x32 on 4096^2, WGS-Leonardo with computational_spot feedback, 3 iterations
+    against OracleSpotHologram (_spots.py:1573-1624, analysis/__init__.py:61-204)."""
+    from oracle import gs_oracle
+    from slmsuite_b200 import SpotHologram
+
+    shape = (4096, 4096)
+    phase = np.random.default_rng(12).uniform(-np.pi, np.pi, shape).astype(np.float32)
+    kw = dict(method="WGS-Leonardo", maxiter=3, verbose=False, feedback="computational_spot")
+    a = SpotHologram.make_rectangular_array(shape, array_shape=(32, 32), array_pitch=(64, 64), basis="knm")
+    a.reset_phase(phase)
+    a.optimize(**kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        b = gs_oracle.OracleSpotHologram.make_rectangular_array(shape, array_shape=(32, 32), array_pitch=(64, 64), basis="knm")
+        b.reset_phase(phase)
+        b.optimize(**kw)
+    assert rel_rmse(a.amp_ff, b.amp_ff) <= 1e-5
+    assert rel_rmse(a.weights, b.weights) <= 1e-5
+    nf = np.abs(b.nearfield)
+    assert _phase_rms(a.phase, b.phase, nf > 1e-4 * nf.max()) <= 2e-5
+
+
+@pytest.mark.slow
+def test_config5_8192_10k_spots_vs_oracle(cuda):
+    """BASELINE configs[4]: SpotHologram 10k random spots on 8192^2, WGS-Leonardo with computational_spot feedback,
+    2 iterations against the oracle (about a minute of host time)."""
+    from oracle import gs_oracle
+    from slmsuite_b200 import SpotHologram
+
+    shape = (8192, 8192)
+    v = np.random.default_rng(5).uniform(64, 8192 - 64, (2, 10000))
+    phase = np.random.default_rng(13).uniform(-np.pi, np.pi, shape).astype(np.float32)
+    kw = dict(method="WGS-Leonardo", maxiter=2, verbose=False, feedback="computational_spot")
+    a = SpotHologram(shape, v, basis="knm")
+    a.reset_phase(phase)
+    a.optimize(**kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        b = gs_oracle.OracleSpotHologram(shape, v, basis="knm")
+        b.reset_phase(phase)
+        b.optimize(**kw)
+    assert rel_rmse(a.amp_ff, b.amp_ff) <= 1e-5
+    assert rel_rmse(a.weights, b.weights) <= 1e-5
+
+
+def test_config4_batch_member_vs_oracle(cuda):
+    """BASELINE configs[3]: one hologram of a 2048^2 GS batch (100 unit spots, default_rng(100 + b) / (200 + b)) against
+    the ORACLE, not against this library's own single-hologram path."""
+    from oracle import gs_oracle
+    from slmsuite_b200 import HologramBatch
+
+    B, N = 4, 2048
+    T = np.stack([_spots((N, N), 100, 100 + b) for b in range(B)])
+    P = np.stack([np.random.default_rng(200 + b).uniform(-np.pi, np.pi, (N, N)).astype(np.float32) for b in range(B)])
+    hb = HologramBatch(T, phase=P)
+    hb.optimize("GS", maxiter=5, verbose=False)
+    amp, ph = hb.amp_ff, hb.phase
+    for b in (1, 3):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            o = gs_oracle.OracleHologram(T[b], phase=P[b])
+            o.optimize("GS", maxiter=5, verbose=False)
+        assert rel_rmse(amp[b], o.amp_ff) <= 1e-5
+        nf = np.abs(o.nearfield)
+        assert _phase_rms(ph[b], o.phase, nf > 1e-4 * nf.max()) <= 2e-5

@@ -173,6 +173,23 @@ struct slmgs_ctx {
     bool use_pdl;
     bool prefetch;
     bool pairs;                // fld is stored row-pair interleaved (slmgs_kernels.h, RowArgs)
+    // CUDA graphs of whole slmgs_run launch sequences (small fields are launch bound): see slmgs_run
+    int launch_mode;           // 0 = launch, 1 = dry run: fold every kernel's arguments into `hash` instead
+    unsigned long long hash;
+    bool use_graphs;
+#ifndef SLMGS_EMULATE
+    struct GraphEntry {
+        unsigned long long key;
+        cudaGraphExec_t exec;
+        int w_pending_out;
+        long long launches;
+        unsigned long long last_use;
+    };
+    std::vector<GraphEntry> graphs;
+    std::vector<unsigned long long> graph_seen;   // keys run once eagerly (lazy allocations done): captured next time
+    std::vector<unsigned long long> graph_bad;    // keys whose capture failed
+    unsigned long long graph_clock;
+#endif
     // persistent fused column kernel with TMA-staged tiles (ColKernelP)
     bool colp;                 // used for COL_FUSED launches of this context
     bool colp_dense;           // slm rows == padded rows
@@ -421,6 +438,12 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
     c->last_sparse = false;
     c->sref = nullptr;
     c->profiling = false;
+    c->launch_mode = 0;
+    c->hash = 0;
+    c->use_graphs = env_int("SLMGS_GRAPHS", 0) != 0;  // opt-in: measured SLOWER than the PDL stream launches on B200
+#ifndef SLMGS_EMULATE
+    c->graph_clock = 0;
+#endif
     c->colp = false;
     c->colp_dense = false;
     c->tmap_dev = nullptr;
@@ -494,6 +517,8 @@ extern "C" int slmgs_destroy(slmgs_ctx* c) {
     for (void* p : ptrs)
         if (p) rt_free(p);
 #ifndef SLMGS_EMULATE
+    for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
+    c->graphs.clear();
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -674,8 +699,15 @@ extern "C" int slmgs_reset_weights(slmgs_ctx* c) {
     c->w_pending = -1;
     if (!c->tiles_dirty && !c->tile_flags_h.empty()) {
         // weights := nan_to_num(target): their occupancy is the target's (flag bit 2), already known -- no device pass
-        for (int& f : c->tile_flags_h) f = (f & ~1) | ((f & 4) ? 1 : 0);
-        c->tile_key = -1;
+        // (the device lists are only rebuilt when that changes a flag: a reset between two runs on the same target
+        // keeps them, so the next slmgs_run issues no copy and never synchronises)
+        bool changed = false;
+        for (int& f : c->tile_flags_h) {
+            const int g = (f & ~1) | ((f & 4) ? 1 : 0);
+            changed = changed || g != f;
+            f = g;
+        }
+        if (changed) c->tile_key = -1;
     } else {
         c->tiles_dirty = true;
     }
@@ -830,8 +862,20 @@ static void prof_mark(slmgs_ctx* c, int klass, bool begin) {
     (void)c; (void)klass; (void)begin;
 #endif
 }
+static void hash_mix(slmgs_ctx* c, const void* data, size_t n) {  // FNV-1a
+    const unsigned char* p = (const unsigned char*)data;
+    unsigned long long h = c->hash;
+    for (size_t i = 0; i < n; ++i) h = (h ^ p[i]) * 1099511628211ull;
+    c->hash = h;
+}
 static int run_row(slmgs_ctx* c, int mode, const RowArgs& a) {
     c->launches++;
+    if (c->launch_mode == 1) {
+        const int g[4] = {mode, c->row_gx, c->B, c->row_threads};
+        hash_mix(c, g, sizeof g);
+        hash_mix(c, &a, sizeof a);
+        return 0;
+    }
     prof_mark(c, mode, true);
     int e = rt_check(c, launch_row(c->W, mode, c->row_gx, c->B, c->row_threads, c->stream, a), "row kernel launch");
     prof_mark(c, mode, false);
@@ -839,6 +883,12 @@ static int run_row(slmgs_ctx* c, int mode, const RowArgs& a) {
 }
 static int run_col(slmgs_ctx* c, int mode, const ColArgs& a) {
     c->launches++;
+    if (c->launch_mode == 1) {
+        const int g[6] = {16 + mode, a.tiles ? c->n_active : c->col_gx, c->B, c->col_threads, c->colp ? 1 : 0, c->sms};
+        hash_mix(c, g, sizeof g);
+        hash_mix(c, &a, sizeof a);
+        return 0;
+    }
     prof_mark(c, 3 + mode, true);
     // compile-time specialisation of the fused constraint (slmgs_kernels.h, VAR_*)
     int var = VAR_GENERAL;
@@ -1026,20 +1076,114 @@ extern "C" int slmgs_sparse_info(const slmgs_ctx* c, int* out3) {
     return SLMGS_OK;
 }
 
-static int run_impl(slmgs_ctx* c, const slmgs_params* params, int n_iter);
+
+static int run_prepare(slmgs_ctx* c, const slmgs_params* params, int n_iter);
+static int run_body(slmgs_ctx* c, const slmgs_params* params, int n_iter);
+static int populate_body(slmgs_ctx* c);
+
+// The launch sequence of a whole run (first row pass, n_iter x (column kernel, row kernel) [+ pre-passes],
+// _populate_results) only depends on host state.  Small fields are launch bound (512^2: ~7 us of host time per
+// launch against kernels of a few us), so a sequence that is run a second time with bit-identical kernel arguments is
+// captured into a CUDA graph -- programmatic-dependent-launch edges included -- and replayed from then on.  The key is
+// a hash over every kernel's argument block from a dry run of the same code that issues the launches.
+#ifndef SLMGS_EMULATE
+static bool graph_eligible(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
+    if (!c->use_graphs || c->profiling || n_iter < 1) return false;
+    for (int i = 0; i < n_iter; ++i) {
+        const slmgs_params* p = params + i;
+        if (!p->update_weights) continue;
+        if (p->feedback != 0) return false;                                   // spot feedback: element-wise kernels + scratch
+        if (p->mraf && (p->zero_weights || p->method == SLMGS_WGS_NOGRETTE)) return false;  // element-wise route
+    }
+    return true;
+}
+static bool key_in(const std::vector<unsigned long long>& v, unsigned long long k) {
+    for (unsigned long long x : v) if (x == k) return true;
+    return false;
+}
+#endif
+
+// first row pass + iterations [+ _populate_results, which sees the whole far field]; leaves sparse_now as it found it
+static int run_sequence(slmgs_ctx* c, const slmgs_params* params, int n_iter, int populate) {
+    const bool sp = c->sparse_now;
+    int e = run_body(c, params, n_iter);
+    c->sparse_now = false;
+    if (!e && populate) e = populate_body(c);
+    c->sparse_now = sp;
+    return e;
+}
 
 extern "C" int slmgs_run(slmgs_ctx* c, const slmgs_params* params, int n_iter, int populate) {
     CHECK_CTX(c);
-    int e = run_impl(c, params, n_iter);
+    int e = run_prepare(c, params, n_iter);
+    bool done = false;
+#ifndef SLMGS_EMULATE
+    if (!e && graph_eligible(c, params, n_iter)) {
+        // dry run: hash of every launch of the sequence, and the host state it leaves behind
+        const int w_in = c->w_pending;
+        const long long l_in = c->launches;
+        c->launch_mode = 1;
+        c->hash = 1469598103934665603ull ^ (populate ? 0x9e3779b97f4a7c15ull : 0ull);
+        e = run_sequence(c, params, n_iter, populate);
+        c->launch_mode = 0;
+        const unsigned long long key = c->hash;
+        const int w_out = c->w_pending;
+        const long long n_launch = c->launches - l_in;
+        c->w_pending = w_in;
+        c->launches = l_in;
+        slmgs_ctx::GraphEntry* hit = nullptr;
+        if (!e) {
+            for (auto& g : c->graphs)
+                if (g.key == key) hit = &g;
+        }
+        if (!e && !hit && key_in(c->graph_seen, key) && !key_in(c->graph_bad, key)) {
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+            if (ok) {
+                const int be = run_sequence(c, params, n_iter, populate);
+                ok = cudaStreamEndCapture(c->stream, &graph) == cudaSuccess && !be && graph;
+            }
+            if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+            c->w_pending = w_in;
+            c->launches = l_in;
+            if (ok) {
+                if (c->graphs.size() >= 16) {  // evict the least recently used
+                    size_t lru = 0;
+                    for (size_t i = 1; i < c->graphs.size(); ++i)
+                        if (c->graphs[i].last_use < c->graphs[lru].last_use) lru = i;
+                    cudaGraphExecDestroy(c->graphs[lru].exec);
+                    c->graphs.erase(c->graphs.begin() + lru);
+                }
+                c->graphs.push_back({key, exec, w_out, n_launch, 0});
+                hit = &c->graphs.back();
+            } else {
+                cudaGetLastError();
+                c->err.clear();
+                c->graph_bad.push_back(key);
+            }
+        }
+        if (hit) {
+            hit->last_use = ++c->graph_clock;
+            e = rt_check(c, (int)cudaGraphLaunch(hit->exec, c->stream), "graph launch");
+            c->w_pending = hit->w_pending_out;
+            c->launches += hit->launches;
+            done = true;
+        } else if (!e && !key_in(c->graph_seen, key)) {
+            if (c->graph_seen.size() >= 64) c->graph_seen.erase(c->graph_seen.begin());
+            c->graph_seen.push_back(key);
+        }
+    }
+#endif
+    if (!e && !done) e = run_sequence(c, params, n_iter, populate);
     c->last_sparse = c->sparse_now;
-    c->sparse_now = false;  // _populate_results and every stepped entry point see the whole far field
-    c->ff_valid = false;
-    if (e) return e;
-    if (populate) return slmgs_populate(c);
-    return SLMGS_OK;
+    c->sparse_now = false;  // every stepped entry point sees the whole far field
+    c->ff_valid = (!e && populate) ? (c->farfield != nullptr) : false;
+    return e;
 }
 
-static int run_impl(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
+static int run_prepare(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
     if (n_iter < 0) return fail(c, SLMGS_ERR_INVALID, "n_iter < 0");
     if (n_iter > 0 && !params) return fail(c, SLMGS_ERR_INVALID, "params is NULL");
     for (int i = 0; i < n_iter; ++i) {
@@ -1049,8 +1193,11 @@ static int run_impl(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
         if (params[i].update_weights && params[i].feedback == 1 && c->n_spots < 1)
             return fail(c, SLMGS_ERR_STATE, "spot feedback without slmgs_set_spots");
     }
+    return prepare_sparse(c, params, n_iter);
+}
+
+static int run_body(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
     int e;
-    if ((e = prepare_sparse(c, params, n_iter))) return e;
     if (n_iter > 0) {
         // a weight update is done inside the fused kernel when it has no global dependency within the
         // iteration (the L2 renormalisation is deferred by one kernel, see DESIGN.md "Lazy normalisation")
@@ -1165,11 +1312,14 @@ extern "C" int slmgs_forward(slmgs_ctx* c) {
     return SLMGS_OK;
 }
 
-extern "C" int slmgs_populate(slmgs_ctx* c) {
-    CHECK_CTX(c);
+static int populate_body(slmgs_ctx* c) {
     // after a fused run `fld` already holds the row transform of the new near field only if the last
     // kernel was ROW_FUSED; rebuilding from the stored phase is always valid and costs one row pass.
-    int e = forward_impl(c, c->farfield ? 1 : 0, 1, 1, true);
+    return forward_impl(c, c->farfield ? 1 : 0, 1, 1, true);
+}
+extern "C" int slmgs_populate(slmgs_ctx* c) {
+    CHECK_CTX(c);
+    int e = populate_body(c);
     if (e) return e;
     c->ff_valid = c->farfield != nullptr;
     return SLMGS_OK;

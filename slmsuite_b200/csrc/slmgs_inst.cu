@@ -34,6 +34,10 @@ template <int LI> static int launch_row_li(int mode, int gx, int gy, int nthread
                 typedef RowKernel<SLMGS_N, ROW_FUSED, true, false, LI> K;
                 return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
             }
+            if (a.h == a.H && a.w == a.W && !a.amp) {  // dense field, scalar source amplitude: the hot loop of the metric
+                typedef RowKernel<SLMGS_N, ROW_FUSED, false, false, LI, true> K;
+                return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
+            }
             typedef RowKernel<SLMGS_N, ROW_FUSED, false, false, LI> K;
             return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
         }
@@ -66,12 +70,25 @@ int SLMGS_CAT(launch_row_, SLMGS_N)(int mode, int gx, int gy, int nthreads, rt_s
 template <int MODE, int VAR> static int launch_col_ct(int gx, int gy, int nthreads, rt_stream s, const ColArgs& a) {
     typedef Fft<SLMGS_N> F;
     constexpr int MAXT = 16384 / F::E;
+    constexpr bool DENSE_VARIANTS = MODE == COL_FUSED && SLMGS_N >= 1024;  // (dense specialisation of the hot kernels only)
     if (nthreads == MAXT) {
+        if constexpr (DENSE_VARIANTS) {
+            if (a.h == a.H) {
+                typedef ColKernel<SLMGS_N, MODE, VAR, MAXT / F::TPL, true> K;
+                return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
+            }
+        }
         typedef ColKernel<SLMGS_N, MODE, VAR, MAXT / F::TPL> K;
         return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
     }
     if constexpr (MAXT / F::TPL >= 2) {
-        if (nthreads == MAXT / 2) {  // half-size blocks (two per SM) for zero-padded problems
+        if (nthreads == MAXT / 2) {  // half-size blocks (two per SM)
+            if constexpr (DENSE_VARIANTS) {
+                if (a.h == a.H) {
+                    typedef ColKernel<SLMGS_N, MODE, VAR, MAXT / F::TPL / 2, true> K;
+                    return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
+                }
+            }
             typedef ColKernel<SLMGS_N, MODE, VAR, MAXT / F::TPL / 2> K;
             return launch_kernel<K>(gx, gy, nthreads, K::smem_bytes(nthreads), s, a, a.pdl != 0);
         }

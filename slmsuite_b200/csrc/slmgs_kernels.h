@@ -224,7 +224,9 @@ struct RowArgs {
 // STORE (ROW_FUSED only): this launch also writes the phase (last iteration of a fused run)
 // SPARSE (ROW_FIRST / ROW_FUSED): spectrum columns are filtered through a.colflag
 // LI: lines interleaved in a warp (thread -> line tid % LI): 1 = row-major fld, 2 = row-pair interleaved fld
-template <int N, int MODE, bool STORE = false, bool SPARSE = false, int LI = 1> struct RowKernel {
+// DENSE (ROW_FUSED): the SLM covers the whole padded field and the source amplitude is a scalar -- no row / column
+//        range tests, no amplitude loads: the projection is ~8 instructions per point
+template <int N, int MODE, bool STORE = false, bool SPARSE = false, int LI = 1, bool DENSE = false> struct RowKernel {
     typedef Fft<N> F;
     static constexpr int TRACE_CLASS = 20 + MODE;  // diagnostic builds (-DSLMGS_TRACE)
     typedef RowArgs Args;
@@ -264,7 +266,7 @@ template <int N, int MODE, bool STORE = false, bool SPARSE = false, int LI = 1> 
         const int lines = id.nthreads / F::TPL;
         L.lt = (id.tid % TEAM) / LI;
         L.sr = id.bx * lines + line;
-        L.active = L.sr < a.h;
+        L.active = DENSE || L.sr < a.h;
         L.fr = (L.sr + a.i0 + (a.H >> 1)) & (a.H - 1);
         L.s = smem + (size_t)team * (F::PADN * LI) + id.tid % LI;
         // element k of the row sits at fbase + k * LI
@@ -361,6 +363,18 @@ template <int N, int MODE, bool STORE = false, bool SPARSE = false, int LI = 1> 
     template <bool REBUILD, bool WRITE>
     static SLMGS_DEVICE void project(State& st, const Args& a, const ThreadId& id, const Loc& L) {
         constexpr int R = F::R0;
+        if constexpr (DENSE && REBUILD && !WRITE) {
+            const float am = a.amp_scalar;
+            SLMGS_UNROLL
+            for (int i = 0; i < E; ++i) {
+                const cf z = st.v[i];
+                const float m2 = z.x * z.x + z.y * z.y;
+                const bool nz = m2 > 1.0e-37f;  // flush-to-zero MUFU rsqrt; |z|^2 below 1e-37 counts as zero (phase 0)
+                const float r = fast_rsqrt(m2) * am;
+                st.v[i] = nz ? cscale(z, r) : cmake(am, 0.f);
+            }
+            return;
+        }
         const bool full = a.w == a.W;
         SLMGS_UNROLL
         for (int u = 0; u < E / R; ++u) {
@@ -511,7 +525,8 @@ struct ColArgs {
 
 // CT: columns per tile known at compile time (block of MAXT threads), 0 = derived from blockDim at run time
 // (small problems).  With CT fixed, every shared-memory access is base register + immediate offset.
-template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
+// DENSE: the SLM rows cover the whole column (h == H) -- no row-range tests in the loads / stores
+template <int N, int MODE, int VAR = 0, int CT = 0, bool DENSE = false> struct ColKernel {
     typedef Fft<N> F;
     static constexpr int TRACE_CLASS = 10 + MODE;  // diagnostic builds (-DSLMGS_TRACE)
     typedef ColArgs Args;
@@ -565,7 +580,7 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
     // b is b + (N/R0) m, so the row pointer advances by a constant and the test is one unsigned compare.
     static SLMGS_DEVICE void load_rows(State& st, const Args& a, const Loc& L) {
         constexpr int R = F::R0;
-        const bool full = a.h == a.H;
+        const bool full = DENSE || a.h == a.H;
         const long long step = (long long)(N / R) * a.W;
         SLMGS_UNROLL
         for (int u = 0; u < E / R; ++u) {
@@ -582,7 +597,7 @@ template <int N, int MODE, int VAR = 0, int CT = 0> struct ColKernel {
     }
     static SLMGS_DEVICE void store_rows(State& st, const Args& a, const Loc& L) {
         constexpr int R = F::R0;
-        const bool full = a.h == a.H;
+        const bool full = DENSE || a.h == a.H;
         const long long step = (long long)(N / R) * a.W;
         SLMGS_UNROLL
         for (int u = 0; u < E / R; ++u) {

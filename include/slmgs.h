@@ -39,7 +39,8 @@ typedef enum {
     SLMGS_ERR_INVALID = -1, /* bad argument / unsupported shape */
     SLMGS_ERR_CUDA = -2,    /* CUDA runtime error */
     SLMGS_ERR_OOM = -3,     /* allocation failed */
-    SLMGS_ERR_STATE = -4    /* call sequence error (e.g. constrain without forward) */
+    SLMGS_ERR_STATE = -4,   /* call sequence error (e.g. constrain without forward) */
+    SLMGS_ERR_NCCL = -5     /* NCCL could not be loaded / a collective failed (slmgs_comm_last_error) */
 } slmgs_status;
 
 /* ALGORITHM_DEFAULTS keys, algorithms/_header.py:53-71 */
@@ -230,6 +231,28 @@ SLMGS_API void* slmgs_comp_stream(slmgs_comp*);
 SLMGS_API int slmgs_comp_constrain_far2near(slmgs_comp*, const slmgs_params*);
 SLMGS_API int slmgs_comp_finalize(slmgs_comp*, int populate);
 SLMGS_API int slmgs_comp_timer(slmgs_comp*, int start, float* ms);                        /* CUDA events on the context's stream */
+
+/* ---- multi-GPU: the one collective of the sharded batch path --------------------------------------
+ * A batch of independent holograms shards across GPUs by hologram with no communication inside the loop
+ * (the reference has no batch: a list of Hologram objects); the job ends with ONE all-gather of the final
+ * near-field phases.  NCCL is loaded with dlopen inside the library (no torch.distributed).  Rank 0 creates the unique
+ * id, the caller distributes its 128 bytes (slmsuite_b200/comm.py: TCP rendezvous on MASTER_ADDR / MASTER_PORT), every
+ * rank creates its communicator.  One process per GPU. */
+typedef struct slmgs_comm slmgs_comm;
+SLMGS_API const char* slmgs_comm_last_error(void);
+SLMGS_API int slmgs_comm_nccl_version(void);                                 /* ncclGetVersion, -1 if NCCL is unavailable */
+SLMGS_API int slmgs_comm_unique_id(unsigned char* out128);                   /* ncclGetUniqueId */
+SLMGS_API int slmgs_comm_create(slmgs_comm** out, const unsigned char* id128, int rank, int world, int device);
+SLMGS_API int slmgs_comm_destroy(slmgs_comm*);
+/* every rank contributes per_rank holograms of `elems` floats (ctx holds n_local <= per_rank: a short or empty last shard
+ * is zero padded; ctx may be NULL when n_local == 0) and receives world * per_rank of them: out_host (or NULL) gets the
+ * gathered array, *out_dev (or NULL) its device address (owned by the communicator), *ms (or NULL) the device time of
+ * the collective.  Runs on the context's stream behind the loop's kernels. */
+SLMGS_API int slmgs_allgather_phase(slmgs_ctx*, slmgs_comm*, int n_local, int per_rank, long long elems,
+                                    float* out_host, void** out_dev, float* ms);
+/* in-place sum over ranks of `count` float64 values at a device address, ordered on `stream` (the 16 N-byte exchange of a
+ * pixel-sharded compressed spot hologram, slmgs_comp_facc_ptr) */
+SLMGS_API int slmgs_comm_allreduce_f64(slmgs_comm*, void* dev_ptr, long long count, void* stream);
 
 #ifdef __cplusplus
 }

@@ -130,6 +130,14 @@ SIGNATURES = {
     "slmgs_comp_constrain_far2near": (C.c_int, [_ctx, _pp]),
     "slmgs_comp_finalize": (C.c_int, [_ctx, C.c_int]),
     "slmgs_comp_timer": (C.c_int, [_ctx, C.c_int, _fp]),
+    # multi-GPU collective (NCCL loaded inside the library)
+    "slmgs_comm_last_error": (C.c_char_p, []),
+    "slmgs_comm_nccl_version": (C.c_int, []),
+    "slmgs_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "slmgs_comm_create": (C.c_int, [C.POINTER(_ctx), C.c_char_p, C.c_int, C.c_int, C.c_int]),
+    "slmgs_comm_destroy": (C.c_int, [_ctx]),
+    "slmgs_allgather_phase": (C.c_int, [_ctx, _ctx, C.c_int, C.c_int, C.c_longlong, _fp, C.POINTER(C.c_void_p), _fp]),
+    "slmgs_comm_allreduce_f64": (C.c_int, [_ctx, C.c_void_p, C.c_longlong, C.c_void_p]),
 }
 
 

@@ -5,8 +5,8 @@ launch sequence (``blockIdx.y`` = hologram), and the multi-GPU sharding of a bat
 The reference has no batch: "a batch" there is a Python list of ``Hologram`` objects run one after
 the other.  Each hologram's loop is independent, so a batch shards across GPUs by
 hologram with no communication inside the loop and ONE all-gather of the final phases at the end
-(SURVEY.md 8e).  ``torch.distributed`` is used for that collective only (NCCL on GPUs, gloo in the CPU
-tests); nothing on the iteration path touches torch.
+(SURVEY.md 8e).  That collective is NCCL behind the C ABI (``slmgs_allgather_phase``, NCCL loaded with dlopen inside
+``libslmgs.so``); the rendezvous is ``slmsuite_b200.comm`` -- no torch anywhere in the package.
 """
 
 import numpy as np
@@ -156,80 +156,46 @@ class HologramBatch(Hologram):
             stats["computational"] = {k: np.array([d[k] for d in per]) for k in per[0]}
 
     # ---- multi-GPU ----------------------------------------------------------------------------
-    def gather_phases(self, n_total=None):
+    def gather_phases(self, n_total=None, comm=None):
         """
-        All-gather of the final near-field phases over the default ``torch.distributed`` process group
-        (one collective per job).  Returns a host array (n_total, h, w) on every rank.  Without an
-        initialised process group this is just ``self.phase``.
+        All-gather of the final near-field phases over the job's ranks (one collective per job): NCCL, loaded inside
+        ``libslmgs.so`` (``slmgs_allgather_phase``); the rendezvous is ``slmsuite_b200.comm`` (no torch).  Returns a
+        host array (n_total, h, w) on every rank.  A single process just returns ``self.phase``.
+        ``comm``: a ``slmsuite_b200.comm.Comm`` (default: the one built from the launcher's environment), or any object
+        with the same ``allgather_phase(holo, n_total)`` method.
         """
-        import torch
-        import torch.distributed as dist
+        from . import comm as _comm
 
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        comm = comm if comm is not None else _comm.default()
+        if comm.world == 1:
             return self.phase
-        world = dist.get_world_size()
-        n_total = int(n_total) if n_total is not None else self._B * world
-        per = -(-n_total // world)
-        h, w = self.slm_shape
-        if dist.get_backend() == "nccl":
-            class _Dev:
-                pass
-
-            view = _Dev()
-            view.__cuda_array_interface__ = {
-                "shape": (self._B, h, w), "typestr": "<f4", "version": 3,
-                "data": (int(self._lib.slmgs_phase_device_ptr(self._ctx)), False)}
-            self._check(self._lib.slmgs_sync(self._ctx))
-            dev = torch.device("cuda", self._device)
-            src = torch.as_tensor(view, device=dev)
-            if self._B < per:
-                pad = torch.zeros((per, h, w), dtype=torch.float32, device=dev)
-                pad[: self._B] = src
-                src = pad
-            out = torch.empty((world * per, h, w), dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(out, src.contiguous())
-            return out[:n_total].cpu().numpy()
-        src = torch.zeros((per, h, w), dtype=torch.float32)
-        src[: self._B] = torch.from_numpy(self.phase)
-        outs = [torch.empty_like(src) for _ in range(world)]
-        dist.all_gather(outs, src)
-        return torch.cat(outs)[:n_total].numpy()
+        return comm.allgather_phase(self, n_total=n_total)
 
 
-def optimize_sharded(targets, phases, method="GS", maxiter=20, slm_shape=None, amp=None, device=None, **kwargs):
+def optimize_sharded(targets, phases, method="GS", maxiter=20, slm_shape=None, amp=None, device=None, comm=None,
+                     **kwargs):
     """
-    Optimise a batch of independent holograms sharded over the ranks of the default process group
-    (one process per GPU): rank r builds a ``HologramBatch`` of its contiguous block, runs the loop with
-    no communication, and all ranks receive all final phases from one all-gather.
-    Returns (phases (B, h, w), local HologramBatch or None if this rank owns nothing).
+    Optimise a batch of independent holograms sharded over the ranks of a job (one process per GPU): rank r builds a
+    ``HologramBatch`` of its contiguous block, runs the loop with no communication, and all ranks receive all final
+    phases from ONE all-gather.  Returns (phases (B, h, w), local HologramBatch or None if this rank owns nothing).
     """
-    import torch.distributed as dist
+    from . import comm as _comm
 
+    comm = comm if comm is not None else _comm.default()
     targets = np.asarray(targets)
     phases = np.asarray(phases)
     n = phases.shape[0]
-    rank = dist.get_rank() if dist.is_initialized() else 0
-    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank, world = comm.rank, comm.world
     lo, hi = shard_bounds(n, rank, world)
     if device is None:
-        device = rank
-    per = -(-n // world)
+        device = getattr(comm, "device", rank)
+    holo = None
     if hi > lo:
         t = targets if targets.ndim == 2 else targets[lo:hi]
         a = amp if (amp is None or np.ndim(amp) == 2) else np.asarray(amp)[lo:hi]
         holo = HologramBatch(t, amp=a, phase=phases[lo:hi], slm_shape=slm_shape, device=device, batch=hi - lo)
         holo.optimize(method, maxiter=maxiter, verbose=False, **kwargs)
-        return holo.gather_phases(n_total=n) if world > 1 else holo.phase, holo
+        if world == 1:
+            return holo.phase, holo
     # a rank without work still takes part in the collective
-    import torch
-
-    h, w = phases.shape[-2:]
-    src = torch.zeros((per, h, w), dtype=torch.float32)
-    if dist.get_backend() == "nccl":
-        src = src.cuda(device)
-        out = torch.empty((world * per, h, w), dtype=torch.float32, device=src.device)
-        dist.all_gather_into_tensor(out, src)
-        return out[:n].cpu().numpy(), None
-    outs = [torch.empty_like(src) for _ in range(world)]
-    dist.all_gather(outs, src)
-    return torch.cat(outs)[:n].numpy(), None
+    return comm.allgather_phase(holo, n_total=n, shape=phases.shape[-2:]), holo

@@ -393,7 +393,9 @@ class CompressedSpotHologram(Hologram):
         mraf = self._mraf_enabled()
         if "WGS" in self.flags["method"]:
             self._check_feedback()
-        if callback is None:
+        # the fused replay is legal when nothing on the host reads the far field between the maps (as Hologram._fusable):
+        # raw_stats / statistics groups need the far field of every iteration
+        if callback is None and not self.flags.get("raw_stats", False) and len(self.flags["stat_groups"]) == 0:
             plist = []
             for _ in iterations:
                 self._update_stats(self.flags["stat_groups"])
@@ -405,7 +407,7 @@ class CompressedSpotHologram(Hologram):
             for _ in iterations:
                 self._check(self._lib.slmgs_comp_forward(self._ctx, 0))  # so the callback sees farfield / amp_ff
                 self._amp_ff_set = True
-                if callback(self):
+                if callback is not None and callback(self):
                     break
                 self._update_stats(self.flags["stat_groups"])
                 params = self._iteration_params(mraf, stepped=True)
@@ -417,55 +419,6 @@ class CompressedSpotHologram(Hologram):
 
 
 # --------------------------------------------------------------------------- one hologram on several GPUs
-class TorchComm:
-    """
-    The two collectives a pixel-sharded compressed hologram needs, over ``torch.distributed`` (NCCL between GPUs; gloo
-    for the CPU test-suite, where the "device" buffers of the emulation library are host memory).  Plumbing only.
-    """
-
-    def __init__(self, group=None):
-        import torch
-        import torch.distributed as dist
-
-        self.torch, self.dist, self.group = torch, dist, group
-        self.rank = dist.get_rank(group)
-        self.world = dist.get_world_size(group)
-
-    def allreduce_f64(self, ptr, count, on_device, device, stream_ptr=None):
-        """In-place sum over ranks of ``count`` float64 values at ``ptr``.  On the device the collective is ordered
-        on the library's own stream (``torch.cuda.ExternalStream``): the process group waits for that stream's
-        pending kernels and the stream waits for the collective -- no host synchronisation."""
-        torch = self.torch
-        if on_device:
-            class _Dev:
-                __cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
-
-            t = torch.as_tensor(_Dev(), device=torch.device("cuda", device))
-            if stream_ptr:
-                with torch.cuda.stream(torch.cuda.ExternalStream(int(stream_ptr), device=torch.device("cuda", device))):
-                    self.dist.all_reduce(t, group=self.group)
-            else:
-                self.dist.all_reduce(t, group=self.group)
-                torch.cuda.current_stream(device).synchronize()
-        else:
-            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(count,))
-            t = torch.from_numpy(a)
-            self.dist.all_reduce(t, group=self.group)
-
-    def allgather_rows(self, local, rows_per_rank, on_device, device):
-        """Concatenate the row slabs of every rank (slabs may differ in height)."""
-        torch = self.torch
-        hmax = max(rows_per_rank)
-        pad = np.zeros((hmax,) + local.shape[1:], dtype=local.dtype)
-        pad[:local.shape[0]] = local
-        t = torch.from_numpy(pad)
-        if on_device:
-            t = t.cuda(device)
-        out = [torch.empty_like(t) for _ in range(self.world)]
-        self.dist.all_gather(out, t, group=self.group)
-        return np.concatenate([o.cpu().numpy()[:r] for o, r in zip(out, rows_per_rank)], axis=0)
-
-
 class ShardedCompressedSpotHologram(CompressedSpotHologram):
     """
     ONE compressed spot hologram spread over several GPUs (not in the reference, whose kernels are single-GPU).
@@ -474,12 +427,17 @@ class ShardedCompressedSpotHologram(CompressedSpotHologram):
     over pixels, so after the local pass the ranks all-reduce the N complex accumulators (16 N bytes -- the only
     exchange of an iteration), run the identical N-vector stage (normalisation, WGS update, WGS-Kim phase, MRAF) and
     project their own slab.  ``phase`` / ``get_phase()`` gather the slabs.  Same constructor as
-    ``CompressedSpotHologram`` plus ``comm`` (default: ``TorchComm()`` on the default process group).
+    ``CompressedSpotHologram`` plus ``comm`` (default: ``slmsuite_b200.comm.default()``: NCCL behind the C ABI on GPUs;
+    any object with the same ``rank`` / ``world`` / ``allreduce_f64`` / ``allgather_rows`` interface works).
     """
 
     def __init__(self, spot_vectors, basis="kxy", spot_amp=None, cameraslm=None, cuda=False, slm_grid=None,
                  zernike_scaling=None, amp=None, phase=None, device=0, comm=None, **kwargs):
-        self._comm = comm if comm is not None else TorchComm()
+        if comm is None:
+            from . import comm as _comm
+
+            comm = _comm.default()
+        self._comm = comm
         rank, world = self._comm.rank, self._comm.world
         if cameraslm is not None:
             slm = cameraslm.slm if hasattr(cameraslm, "slm") else cameraslm

@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -134,6 +135,8 @@ struct slmgs_ctx {
     int* spot_y;
     float* spot_amp;
     double* spot_pw;
+    float* spot_wn;            // [B][N] updated spot weights before the scatter
+    unsigned char* spot_keep;  // [N] last spot of every pixel
     int n_spots;
     // host-side state
     float amp_scalar;
@@ -413,6 +416,7 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
     c->twA_row = c->twB_row = c->twA_col = c->twB_col = nullptr;
     c->acc = nullptr; c->partial = nullptr; c->winf = nullptr;
     c->spot_x = c->spot_y = nullptr; c->spot_amp = nullptr; c->spot_pw = nullptr; c->n_spots = 0;
+    c->spot_wn = nullptr; c->spot_keep = nullptr;
     c->amp_scalar = (float)(1.0 / sqrt((double)h * (double)w));
     c->amp_per_hologram = 0;
     c->amp_count = 0;
@@ -511,7 +515,7 @@ extern "C" int slmgs_destroy(slmgs_ctx* c) {
     if (c->stream) rt_sync(c->stream);
     void* ptrs[] = {c->fld, c->farfield, c->stage_c, c->stage_f, c->phase, c->amp, c->prop, c->target,
                     c->weights, c->phase_ff, c->amp_ff, c->twA_row, c->twB_row, c->twA_col, c->twB_col, c->acc,
-                    c->partial, c->spot_x, c->spot_y, c->spot_amp, c->spot_pw, c->phase_saved, c->mp_sum, c->zero_w,
+                    c->partial, c->spot_x, c->spot_y, c->spot_amp, c->spot_pw, c->spot_wn, c->spot_keep, c->phase_saved, c->mp_sum, c->zero_w,
                     c->tile_flags, c->tile_list, c->tile_byte, c->tile_count, c->samp_y, c->samp_x, c->scratch, c->winf,
                     c->tmap_dev};
     for (void* p : ptrs)
@@ -1428,15 +1432,39 @@ extern "C" int slmgs_set_spots(slmgs_ctx* c, int n, const int* x, const int* y, 
     for (int i = 0; i < n; ++i)
         if (x[i] < 0 || x[i] >= c->W || y[i] < 0 || y[i] >= c->H) return fail(c, SLMGS_ERR_INVALID, "spot outside the computational space");
     RT(c, rt_sync(c->stream));
-    if (c->spot_x) { rt_free(c->spot_x); rt_free(c->spot_y); rt_free(c->spot_amp); rt_free(c->spot_pw); c->spot_x = nullptr; }
+    auto drop_spots = [&]() {
+        void** ps[] = {(void**)&c->spot_x, (void**)&c->spot_y, (void**)&c->spot_amp, (void**)&c->spot_pw, (void**)&c->spot_wn,
+                       (void**)&c->spot_keep};
+        for (void** q : ps) {
+            if (*q) rt_free(*q);
+            *q = nullptr;
+        }
+        c->n_spots = 0;
+    };
+    drop_spots();
     int e;
-    if ((e = dev_alloc(c, &c->spot_x, (size_t)n))) return e;
-    if ((e = dev_alloc(c, &c->spot_y, (size_t)n))) return e;
-    if ((e = dev_alloc(c, &c->spot_amp, (size_t)n))) return e;
-    if ((e = dev_alloc(c, &c->spot_pw, (size_t)n * c->B))) return e;
+    if ((e = dev_alloc(c, &c->spot_x, (size_t)n)) || (e = dev_alloc(c, &c->spot_y, (size_t)n)) ||
+        (e = dev_alloc(c, &c->spot_amp, (size_t)n)) || (e = dev_alloc(c, &c->spot_pw, (size_t)n * c->B)) ||
+        (e = dev_alloc(c, &c->spot_wn, (size_t)n * c->B)) || (e = dev_alloc(c, &c->spot_keep, (size_t)n))) {
+        drop_spots();
+        return e;
+    }
+    // two spots may round to the same pixel: the reference scatters the N-vector with a fancy index (_spots.py:1622-1624),
+    // where the LAST occurrence wins
+    std::vector<unsigned char> keep((size_t)n, 1);
+    {
+        std::vector<long long> key((size_t)n);
+        for (int i = 0; i < n; ++i) key[i] = (long long)y[i] * c->W + x[i];
+        std::vector<int> order((size_t)n);
+        for (int i = 0; i < n; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+        for (int i = 0; i + 1 < n; ++i)
+            if (key[order[i]] == key[order[i + 1]]) keep[order[i]] = 0;  // a later spot owns the pixel
+    }
     RT(c, rt_h2d(c->spot_x, x, (size_t)n * sizeof(int), c->stream));
     RT(c, rt_h2d(c->spot_y, y, (size_t)n * sizeof(int), c->stream));
     RT(c, rt_h2d(c->spot_amp, spot_amp, (size_t)n * sizeof(float), c->stream));
+    RT(c, rt_h2d(c->spot_keep, keep.data(), (size_t)n, c->stream));
     c->n_spots = n;
     c->spot_x_h.assign(x, x + n);
     c->tile_key = -1;
@@ -1447,7 +1475,7 @@ static SpotArgs spot_args(slmgs_ctx* c, int width) {
     SpotArgs a;
     memset(&a, 0, sizeof a);
     a.img = c->amp_ff; a.weights = c->weights; a.sx = c->spot_x; a.sy = c->spot_y; a.spot_amp = c->spot_amp;
-    a.pw = c->spot_pw; a.img_bs = (long long)c->H * c->W; a.H = c->H; a.W = c->W; a.N = c->n_spots; a.width = width;
+    a.pw = c->spot_pw; a.wn = c->spot_wn; a.keep = c->spot_keep; a.img_bs = (long long)c->H * c->W; a.H = c->H; a.W = c->W; a.N = c->n_spots; a.width = width;
     a.C = c->col_threads / c->icol.tpl;
     return a;
 }
@@ -1667,11 +1695,14 @@ extern "C" int slmgs_window_power(slmgs_ctx* c, int n, const int* x, const int* 
             return fail(c, SLMGS_ERR_INVALID, "index out of bounds in window integration");
     }
     int e;
-    int *dx = nullptr, *dy = nullptr;
-    double* dpw = nullptr;
-    if ((e = dev_alloc(c, &dx, (size_t)n))) return e;
-    if ((e = dev_alloc(c, &dy, (size_t)n))) { rt_free(dx); return e; }
-    if ((e = dev_alloc(c, &dpw, (size_t)n * c->B))) { rt_free(dx); rt_free(dy); return e; }
+    // grow-only scratch (a cudaMalloc / cudaFree pair per call costs milliseconds once the process holds gigabytes, and
+    // this runs every iteration with stat_groups=["computational_spot"])
+    const size_t ib = (((size_t)n * sizeof(int)) + 15) & ~(size_t)15;
+    void* buf = nullptr;
+    if ((e = scratch_reserve(c, 2 * ib + (size_t)n * c->B * sizeof(double), &buf))) return e;
+    int* dx = reinterpret_cast<int*>(buf);
+    int* dy = reinterpret_cast<int*>(reinterpret_cast<char*>(buf) + ib);
+    double* dpw = reinterpret_cast<double*>(reinterpret_cast<char*>(buf) + 2 * ib);
     e = rt_check(c, rt_h2d(dx, x, (size_t)n * sizeof(int), c->stream), "h2d");
     if (!e) e = rt_check(c, rt_h2d(dy, y, (size_t)n * sizeof(int), c->stream), "h2d");
     if (!e) {
@@ -1694,7 +1725,6 @@ extern "C" int slmgs_window_power(slmgs_ctx* c, int n, const int* x, const int* 
             for (int b = 0; b < c->B; ++b) total[b] = acc[(size_t)b * ACC_N + ACC_TMP];
     }
     rt_sync(c->stream);
-    rt_free(dx); rt_free(dy); rt_free(dpw);
     return e;
 }
 

@@ -211,6 +211,8 @@ struct SpotArgs {
     const int* sy;
     const float* spot_amp;  // [N] target amplitudes (host float64 in the reference, rounded once here)
     double* pw;           // [B][N] window powers (output of gather, input of update)
+    float* wn;            // [B][N] updated spot weights before the scatter (the reference's N-vector, _spots.py:1617-1624)
+    const unsigned char* keep;  // [N] 1 = last spot that rounds to its pixel: numpy's fancy-index scatter keeps that one
     long long img_bs;
     int H, W, N, width;
     int C;  // column-tile width of the image layout
@@ -268,6 +270,7 @@ struct SpotUpdateKernel {
         double* scal = sm + id.nthreads;  // 0: sum f^2, 1: sum ratio, 2: sum w^2
         const double* pw = a.pw + (long long)id.by * a.N;
         float* wts = a.weights + (long long)id.by * a.img_bs;
+        float* wn = a.wn + (long long)id.by * a.N;
         WgsParams q = a.wgs;
         if (P == 0) {  // partial sum of feedback^2 (feedback = float32(sqrt(pw)))
             double s = 0.0;
@@ -288,20 +291,21 @@ struct SpotUpdateKernel {
             if (q.method == METHOD_NOGRETTE)
                 for (int n = id.tid; n < a.N; n += id.nthreads) s += (double)wgs_ratio((float)sqrt(pw[n]), a.spot_amp[n], q);
             sm[id.tid] = s;
-        } else if (P == 4) {  // update, partial sum of w^2
+        } else if (P == 4) {  // gather + update on the N-vector (no pixel is written yet: two spots may round to the
+                              // same pixel, and both must start from its old weight), partial sum of w^2
             q.inv_fnorm = (float)(1.0 / sqrt(scal[0]));
             q.neg_inv_mean = -(1.0f / (float)(scal[1] / (double)a.N));
             double s = 0.0;
             for (int n = id.tid; n < a.N; n += id.nthreads) {
-                const long long p = pix(a, n);
-                const float w = wgs_apply(wts[p], wgs_multiplier((float)sqrt(pw[n]), a.spot_amp[n], q));
-                wts[p] = w;
+                const float w = wgs_apply(wts[pix(a, n)], wgs_multiplier((float)sqrt(pw[n]), a.spot_amp[n], q));
+                wn[n] = w;
                 s += (double)w * (double)w;
             }
             sm[id.tid] = s;
-        } else if (P == 6) {  // normalise over the N spots (:1877 on the N-vector)
+        } else if (P == 6) {  // normalise over the N spots (:1877 on the N-vector) and scatter: the last duplicate wins
             const float sc = (float)(1.0 / sqrt(scal[2]));
-            for (int n = id.tid; n < a.N; n += id.nthreads) wts[pix(a, n)] *= sc;
+            for (int n = id.tid; n < a.N; n += id.nthreads)
+                if (a.keep[n]) wts[pix(a, n)] = wn[n] * sc;
         }
     }
 };

@@ -1,6 +1,7 @@
 """HologramBatch (B holograms per launch) and the multi-rank sharding of a batch.
-CPU: host emulation + torch.distributed gloo, world_size 2 (spawned processes).  The same single-rank
-checks run on the GPU library when marked gpu."""
+CPU: host emulation, world_size 2 (spawned processes), once over torch.distributed gloo (tests/_gloo_comm.py) and once
+over the package's own torch-free TCP communicator (slmsuite_b200/comm.py).  The same single-rank checks run on the GPU
+library when marked gpu; the NCCL all-gather behind the C ABI is exercised by bench.py --gpus N."""
 import os
 import socket
 import sys
@@ -72,17 +73,39 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
+    from _gloo_comm import GlooComm
 
     from slmsuite_b200 import _lib, optimize_sharded
 
     _lib.use_library(EMU_LIB)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     T, P, slm = _problem(B=5)
-    phases, local = optimize_sharded(T, P, method="WGS-Leonardo", maxiter=8, slm_shape=slm, device=0)
+    phases, local = optimize_sharded(T, P, method="WGS-Leonardo", maxiter=8, slm_shape=slm, device=0, comm=GlooComm())
     q.put((rank, phases, None if local is None else len(local)))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def _worker_tcp(rank, world, port, q):
+    """the package's own communicator: environment of a torchrun-style launcher, no torch"""
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world),
+                       "LOCAL_RANK": str(rank)})
+    sys.path.insert(0, ROOT)
+    from slmsuite_b200 import _lib, comm, optimize_sharded
+
+    _lib.use_library(EMU_LIB)
+    c = comm.default()
+    assert (c.rank, c.world) == (rank, world) and not c.on_device()
+    B = 3 if world == 4 else 5  # world 4, B 3: the last rank owns nothing and still joins the collective
+    T, P, slm = _problem(B=B)
+    phases, local = optimize_sharded(T, P, method="WGS-Leonardo", maxiter=8, slm_shape=slm, device=0)
+    total = c.allreduce_host(np.array([float(rank + 1)]))
+    c.barrier()
+    q.put((rank, phases, None if local is None else len(local), float(total[0])))
+    c.close()
+    assert "torch" not in sys.modules
 
 
 def test_two_rank_sharding_gloo(emu):
@@ -115,3 +138,40 @@ def test_two_rank_sharding_gloo(emu):
     for rank in (0, 1):
         assert results[rank][0].shape == (5,) + slm
         assert np.allclose(results[rank][0], ref.phase, atol=1e-5)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharding_over_the_package_communicator(emu, world):
+    """slmsuite_b200.comm (TCP rendezvous, no torch): contiguous shards, ONE all-gather, every rank holds every phase."""
+    import multiprocessing as mp
+
+    from slmsuite_b200 import HologramBatch
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_tcp, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = {}
+    for _ in range(world):
+        rank, phases, nlocal, total = q.get(timeout=240)
+        results[rank] = (phases, nlocal, total)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    B = 3 if world == 4 else 5
+    T, P, slm = _problem(B=B)
+    ref = HologramBatch(T, phase=P, slm_shape=slm)
+    ref.optimize("WGS-Leonardo", maxiter=8, verbose=False)
+    if world == 4:
+        assert [results[r][1] for r in range(4)] == [1, 1, 1, None]
+    else:
+        assert [results[r][1] for r in range(2)] == [3, 2]
+    for rank in range(world):
+        assert results[rank][0].shape == (B,) + slm
+        assert np.allclose(results[rank][0], ref.phase, atol=1e-5)
+        assert results[rank][2] == world * (world + 1) / 2

@@ -12,19 +12,16 @@ import time
 import warnings
 
 import numpy as np
-import torch
-import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from slmsuite_b200 import CompressedSpotHologram, _lib  # noqa: E402
+from slmsuite_b200 import CompressedSpotHologram, _lib, comm as slm_comm  # noqa: E402
 from slmsuite_b200.compressed import ShardedCompressedSpotHologram  # noqa: E402
 
 rank = int(os.environ.get("RANK", 0))
 local = int(os.environ.get("LOCAL_RANK", 0))
 world = int(os.environ.get("WORLD_SIZE", 1))
-torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 _lib.use_library(_lib.DEFAULT_LIBRARY)
+cm = slm_comm.default()  # NCCL behind the C ABI (no torch): rendezvous on MASTER_ADDR / MASTER_PORT
 
 n_spots = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 iters = 10
@@ -45,12 +42,12 @@ with warnings.catch_warnings():
     h.reset_phase(phase)
     h.reset(reset_phase=False)
     h.flags["fixed_phase"] = False
-    torch.cuda.synchronize()
-    dist.barrier()
+    h._check(h._lib.slmgs_comp_sync(h._ctx))
+    cm.barrier()
     t0 = time.perf_counter()
     h.optimize(maxiter=iters, **opt)
-    torch.cuda.synchronize()
-    dist.barrier()
+    h._check(h._lib.slmgs_comp_sync(h._ctx))
+    cm.barrier()
     t_sharded = (time.perf_counter() - t0) / iters
 
 if rank == 0:
@@ -62,7 +59,7 @@ if rank == 0:
         one.reset_phase(phase)
         one.reset(reset_phase=False)
         one.flags["fixed_phase"] = False
-        torch.cuda.synchronize()
+        one._check(one._lib.slmgs_comp_sync(one._ctx))
         t0 = time.perf_counter()
         one.optimize(maxiter=iters, **opt)
         one._check(one._lib.slmgs_comp_sync(one._ctx))
@@ -73,5 +70,5 @@ if rank == 0:
           f"{t_sharded*1e3:.3f} ms/iteration vs 1 GPU {t_one*1e3:.3f} ms/iteration -> speed-up {t_one/t_sharded:.2f}; "
           f"spot amplitude rel-RMSE vs single GPU {ea:.1e}, phase rms {np.sqrt(np.mean(d**2)):.1e} rad", flush=True)
     assert ea <= 2e-6 and np.sqrt(np.mean(d ** 2)) <= 5e-5
-dist.barrier()
-dist.destroy_process_group()
+cm.barrier()
+cm.close()

@@ -87,6 +87,18 @@ static int launch_row(int n, int mode, int gx, int gy, int nt, rt_stream s, cons
 #undef X
     return -1;
 }
+static int launch_colt(int n, int var, int dense, int gx, int gy, rt_stream s, const ColArgs& a, const void* tmap) {
+#define X(N_) if (n == N_) return launch_colt_##N_(var, dense, gx, gy, s, a, tmap);
+    SLMGS_FOR_SIZES(X)
+#undef X
+    return -1;
+}
+static int launch_rowt(int n, int store, int dense, int gx, int gy, rt_stream s, const RowArgs& a) {
+#define X(N_) if (n == N_) return launch_rowt_##N_(store, dense, gx, gy, s, a);
+    SLMGS_FOR_SIZES(X)
+#undef X
+    return -1;
+}
 static int launch_colp(int n, int var, int dense, int gx, int gy, int nt, rt_stream s, const ColArgs& a) {
 #define X(N_) if (n == N_) return launch_colp_##N_(var, dense, gx, gy, nt, s, a);
     SLMGS_FOR_SIZES(X)
@@ -194,6 +206,10 @@ struct slmgs_ctx {
     unsigned long long graph_clock;
 #endif
     // persistent fused column kernel with TMA-staged tiles (ColKernelP)
+    // team kernels (slmgs_teams.h): TMA-staged tiles, two compute teams per persistent block
+    bool teams_col, teams_row;  // used for the COL_FUSED / ROW_FUSED launches of the dense-far-field loop
+    int tb_pairs, tb_n, tb_lo, tb_hi0;  // TMA boxes of a column tile (ColArgs)
+    unsigned char tmap_pairs[128] __attribute__((aligned(64)));  // host copy of the CUtensorMap over the row-pair interleaved fld
     bool colp;                 // used for COL_FUSED launches of this context
     bool colp_dense;           // slm rows == padded rows
     void* tmap_dev;            // device copy of the CUtensorMap over fld
@@ -387,6 +403,55 @@ static int make_tensor_map(slmgs_ctx* c) {
     return 0;
 }
 
+// Team column kernel: tensor map over the row-pair interleaved fld seen as {2 W elements, H / 2 row pairs, B} of 8-byte
+// elements, box {2 columns x 2 row parities, tb_pairs row pairs, 1}; and the boxes of a column tile that hold SLM rows.
+// The rolled rows that hold the SLM are [0, lo) and [hi, H) (lo = i0 + h - H/2, hi = i0 + H/2).
+static bool setup_teams_col(slmgs_ctx* c) {
+    const int H = c->H, h = c->h, i0 = c->i0;
+    if (h == H) {
+        c->tb_pairs = 256;
+        if (c->tb_pairs > H / 2) c->tb_pairs = H / 2;
+        c->tb_n = c->tb_lo = (H / 2) / c->tb_pairs;
+        c->tb_hi0 = 0;
+    } else {
+        const int lo = i0 + h - H / 2, hi = i0 + H / 2;  // rows
+        if (lo < 0 || hi > H || (lo & 1) || (hi & 1) || lo > hi) return false;
+        // largest box (power of two, <= 256 row pairs) with at most 64 boxes per tile and little over-fetch
+        int bp = 256;
+        while (bp > 8) {
+            const int nlo = (lo / 2 + bp - 1) / bp, nhi = ((H - hi) / 2 + bp - 1) / bp;
+            const int fetched = (nlo + nhi) * bp * 2;
+            if (fetched * 8 <= h * 9) break;  // <= 12.5 % extra rows
+            bp >>= 1;
+        }
+        const int nlo = (lo / 2 + bp - 1) / bp, nhi = ((H - hi) / 2 + bp - 1) / bp;
+        if (nlo + nhi > 64 || nlo + nhi < 1) return false;
+        c->tb_pairs = bp;
+        c->tb_lo = nlo;
+        c->tb_n = nlo + nhi;
+        c->tb_hi0 = H / 2 - nhi * bp;                      // the high boxes end at the last row pair
+        if (c->tb_hi0 < nlo * bp) return false;            // the two ranges would overlap: not worth a special case
+    }
+#ifndef SLMGS_EMULATE
+    slmgs_encode_fn encode = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&encode, cudaEnableDefault, &qres) != cudaSuccess || !encode) {
+        cudaGetLastError();
+        return false;
+    }
+    static_assert(sizeof(CUtensorMap) <= sizeof(((slmgs_ctx*)0)->tmap_pairs), "tensor map copy");
+    cuuint64_t dims[3] = {(cuuint64_t)c->W * 2, (cuuint64_t)c->H / 2, (cuuint64_t)c->B};
+    cuuint64_t strides[2] = {(cuuint64_t)c->W * 2 * sizeof(cf), (cuuint64_t)c->W * c->H * sizeof(cf)};
+    cuuint32_t box[3] = {4, (cuuint32_t)c->tb_pairs, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    if (encode(reinterpret_cast<CUtensorMap*>(c->tmap_pairs), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, c->fld, dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+#endif
+    return true;
+}
+
 extern "C" int slmgs_version(void) { return 100; }
 
 
@@ -448,6 +513,8 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
 #ifndef SLMGS_EMULATE
     c->graph_clock = 0;
 #endif
+    c->teams_col = c->teams_row = false;
+    c->tb_pairs = c->tb_n = c->tb_lo = c->tb_hi0 = 0;
     c->colp = false;
     c->colp_dense = false;
     c->tmap_dev = nullptr;
@@ -503,6 +570,13 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
         CR(rt_check(c, rt_h2d(c->twB_col, b.data(), b.size() * sizeof(cf), c->stream), "twiddle upload"));
     }
     if (c->colp && make_tensor_map(c)) c->colp = false;  // no TMA descriptor: the plain column kernel takes over
+    // team kernels: row-pair interleaved field, 2-column tiles (the image layout of the context), whole row pairs
+    {
+        const bool on = env_int("SLMGS_TEAMS", 1) != 0 && c->pairs && !c->colp;
+        c->teams_col = on && c->icol.teams && c->col_threads == 2 * c->icol.tpl && (c->h % 2) == 0 && (c->i0 % 2) == 0 &&
+                       setup_teams_col(c);
+        c->teams_row = on && c->irow.teams && (c->h % 2) == 0 && (c->i0 % 2) == 0 && c->H >= 32;
+    }
     CR(rt_check(c, rt_sync(c->stream), "sync"));
 #undef CR
     *out = c;
@@ -846,6 +920,7 @@ static ColArgs col_args(slmgs_ctx* c) {
         a.tiles_bs = c->W / (c->col_threads / c->icol.tpl);
     }
     a.pairs = c->pairs ? 1 : 0;
+    a.tb_pairs = c->tb_pairs; a.tb_n = c->tb_n; a.tb_lo = c->tb_lo; a.tb_hi0 = c->tb_hi0;
     a.tmap = c->tmap_dev;
     a.n_boxes = c->n_boxes;
     memcpy(a.box_slot, c->box_slot, sizeof a.box_slot);
@@ -872,6 +947,15 @@ static void hash_mix(slmgs_ctx* c, const void* data, size_t n) {  // FNV-1a
     for (size_t i = 0; i < n; ++i) h = (h ^ p[i]) * 1099511628211ull;
     c->hash = h;
 }
+// persistent blocks per hologram of a team kernel: the resident blocks of the GPU (a block = two teams of 2 tpl
+// threads) shared by the batch, at most one block per two work items
+static int teams_blocks(slmgs_ctx* c, const LaunchInfo& li, int items) {
+    const int per_sm = 1024 / (4 * li.tpl) > 0 ? 1024 / (4 * li.tpl) : 1;
+    int gx = c->sms * per_sm / c->B;
+    if (gx < 1) gx = 1;
+    if (gx > (items + 1) / 2) gx = (items + 1) / 2;
+    return gx;
+}
 static int run_row(slmgs_ctx* c, int mode, const RowArgs& a) {
     c->launches++;
     if (c->launch_mode == 1) {
@@ -881,7 +965,15 @@ static int run_row(slmgs_ctx* c, int mode, const RowArgs& a) {
         return 0;
     }
     prof_mark(c, mode, true);
-    int e = rt_check(c, launch_row(c->W, mode, c->row_gx, c->B, c->row_threads, c->stream, a), "row kernel launch");
+    int e;
+    if (mode == ROW_FUSED && c->teams_row && !a.colflag) {
+        // persistent: one block (two teams) per SM over the whole batch, each team walking over row pairs
+        int gx = teams_blocks(c, c->irow, (c->h + 1) / 2);
+        const int dense = (a.h == a.H && a.w == a.W && !a.amp) ? 1 : 0;
+        e = rt_check(c, launch_rowt(c->W, a.store_phase, dense, gx, c->B, c->stream, a), "team row kernel launch");
+    } else {
+        e = rt_check(c, launch_row(c->W, mode, c->row_gx, c->B, c->row_threads, c->stream, a), "row kernel launch");
+    }
     prof_mark(c, mode, false);
     return e;
 }
@@ -904,7 +996,11 @@ static int run_col(slmgs_ctx* c, int mode, const ColArgs& a) {
     }
     const int gx = a.tiles ? c->n_active : c->col_gx;
     int e;
-    if (mode == COL_FUSED && c->colp) {
+    if (mode == COL_FUSED && c->teams_col && !a.tiles) {
+        const int pgx = teams_blocks(c, c->icol, c->W / 2);
+        e = rt_check(c, launch_colt(c->H, var, c->h == c->H ? 1 : 0, pgx, c->B, c->stream, a, c->tmap_pairs),
+                     "team column kernel launch");
+    } else if (mode == COL_FUSED && c->colp) {
         // persistent: about one block per SM over the whole batch, each walking over its share of the tiles
         int pgx = c->sms / c->B;
         if (pgx < 1) pgx = 1;

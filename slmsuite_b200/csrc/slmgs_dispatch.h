@@ -1,6 +1,6 @@
 // slmgs_dispatch.h -- per-size launchers (one translation unit per N, see slmgs_inst.cu).
 #pragma once
-#include "slmgs_kernels.h"
+#include "slmgs_teams.h"
 
 namespace slmgs {
 
@@ -20,12 +20,15 @@ struct LaunchInfo {
     int p_npre;      // persistent TMA column kernel (ColKernelP): staged boxes per tile, 0 = not built for this size
     int p_ct;        // ... its tile width (columns) at maxt threads
     int p_box_rows;  // ... rows per box
+    int teams;       // team kernels (slmgs_teams.h: ColKernelT / RowKernelT) are built for this size
 };
 
 #define SLMGS_DECL(N_)                                                                                        \
     int launch_row_##N_(int mode, int gx, int gy, int nthreads, rt_stream s, const RowArgs& a);               \
     int launch_col_##N_(int mode, int var, int gx, int gy, int nthreads, rt_stream s, const ColArgs& a);               \
     int launch_colp_##N_(int var, int dense, int gx, int gy, int nthreads, rt_stream s, const ColArgs& a);             \
+    int launch_colt_##N_(int var, int dense, int gx, int gy, rt_stream s, const ColArgs& a, const void* tmap);         \
+    int launch_rowt_##N_(int store, int dense, int gx, int gy, rt_stream s, const RowArgs& a);                        \
     LaunchInfo launch_info_##N_();
 SLMGS_DECL(16)
 SLMGS_DECL(32)

@@ -33,6 +33,17 @@
 
 namespace slmgs {
 
+// L1-burst hooks of the *_sy stage functions (see below): no-ops outside the ping-pong kernels
+struct NoSync {
+    SLMGS_DEVICE void acquire() {}
+    SLMGS_DEVICE void release() {}
+};
+
+// twiddle tables in shared memory (compact layout, see Fft::twiddle)
+struct SmemTw {
+    const cf* p;
+};
+
 template <int N> struct Plan;
 // E: points per thread; R0,R1,R2: stage radices (smallest first so the two big stages keep 16 consecutive
 // lanes on consecutive addresses); P2: pad of the k0 stride (see "Shared memory layout" below).
@@ -90,6 +101,15 @@ template <int N> struct Fft {
         if (S == 0) return __ldg(twA + m * M1 + b);
         return __ldg(twB + m * R2 + (b % R2));
     }
+    // The same from a compact copy of the tables in shared memory (persistent kernels, slmgs_teams.h): with
+    // SLMGS_TW_PRODUCTS only the rows m = 1, 2, 4, 8 of either table are ever read; row m is stored at log2(m).
+    static constexpr int TWS_ROWS = 4;
+    static constexpr int TWS_A = TWS_ROWS * M1, TWS_B = TWS_ROWS * R2;  // entries of the compact tables
+    static SLMGS_HD int tws_row(int m) { return m == 1 ? 0 : m == 2 ? 1 : m == 4 ? 2 : 3; }
+    template <int S> static SLMGS_DEVICE cf twiddle(SmemTw twA, SmemTw twB, int b, int m) {
+        if (S == 0) return twA.p[tws_row(m) * M1 + b];
+        return twB.p[tws_row(m) * R2 + (b % R2)];
+    }
     // spatial index of element m of first-stage butterfly b / frequency of element m of last-stage butterfly b
     static SLMGS_HD int first_index(int b, int m) { return b + (N / R0) * m; }
     static SLMGS_HD int last_index(int b, int m) { return b + (N / last_radix()) * m; }
@@ -103,8 +123,8 @@ template <int N> struct Fft {
         static constexpr int value = K;
     };
     static constexpr int high_pow2(int g) { return g >= 16 ? 16 : g >= 8 ? 8 : g >= 4 ? 4 : g >= 2 ? 2 : 1; }
-    template <int S, int G, int NG, class Fn>
-    static SLMGS_DEVICE void tw_groups(cf* W, cf w1, cf w2, cf w3, int b, const cf* twA, const cf* twB, Fn& fn) {
+    template <int S, int G, int NG, class Fn, class TP>
+    static SLMGS_DEVICE void tw_groups(cf* W, cf w1, cf w2, cf w3, int b, TP twA, TP twB, Fn& fn) {
         if constexpr (G < NG) {
             constexpr int hp = high_pow2(G);
             if constexpr (hp == G) W[G] = twiddle<S>(twA, twB, b, 4 * G);
@@ -116,13 +136,13 @@ template <int N> struct Fft {
             tw_groups<S, G + 1, NG>(W, w1, w2, w3, b, twA, twB, fn);
         }
     }
-    template <int S, int K, class Fn> static SLMGS_DEVICE void tw_table(int b, const cf* twA, const cf* twB, Fn& fn) {
+    template <int S, int K, class Fn, class TP> static SLMGS_DEVICE void tw_table(int b, TP twA, TP twB, Fn& fn) {
         if constexpr (K < radix<S>()) {
             fn(IC<K>(), twiddle<S>(twA, twB, b, K));
             tw_table<S, K + 1>(b, twA, twB, fn);
         }
     }
-    template <int S, class Fn> static SLMGS_DEVICE void for_each_twiddle(int b, const cf* twA, const cf* twB, Fn fn) {
+    template <int S, class Fn, class TP> static SLMGS_DEVICE void for_each_twiddle(int b, TP twA, TP twB, Fn fn) {
         constexpr int R = radix<S>();
 #ifdef SLMGS_TW_PRODUCTS
         if constexpr (R >= 8) {
@@ -161,7 +181,7 @@ template <int N> struct Fft {
             load_elems<S, U, K + 1>(v, lt, s, si);
         }
     }
-    template <int S, int U> static SLMGS_DEVICE void inv_twiddle_all(cf* v, int lt, const cf* twA, const cf* twB) {
+    template <int S, int U, class TP> static SLMGS_DEVICE void inv_twiddle_all(cf* v, int lt, TP twA, TP twB) {
         constexpr int R = radix<S>();
         for_each_twiddle<S>(lt + TPL * U, twA, twB, [&](auto k, cf w) {
             constexpr int K = decltype(k)::value;
@@ -244,6 +264,77 @@ template <int N> struct Fft {
         if constexpr (U < E / R) {
             unscramble<R, U, 0>(v, o);
             unscramble_all<R, U + 1>(v, o);
+        }
+    }
+
+    // ---- stages with L1-burst hooks (ping-pong teams, slmgs_launch.h: slmgs_kernel_pp) -------------------
+    // Same arithmetic as fwd_stage / inv_stage, ordered as  [shared-memory reads] release | butterflies + twiddles |
+    // acquire [shared-memory writes]:  `sy` brackets the bursts on the L1 / shared-memory data pipe so that two teams
+    // of one block alternate on it (one team's exchange runs under the other's butterflies).  Stage S == 0 of the
+    // forward (S == NS-1 of the inverse) has no read burst: the caller releases after its global loads.
+    template <int S, int U, class TP> static SLMGS_DEVICE void fwd_twiddle_u(cf* v, int lt, TP twA, TP twB) {
+        constexpr int R = radix<S>();
+        if constexpr (U < E / R) {
+            for_each_twiddle<S>(lt + TPL * U, twA, twB, [&](auto k, cf w) {
+                constexpr int K = decltype(k)::value;
+                v[U * R + RegFFT<R>::pos(K)] = cmul(v[U * R + RegFFT<R>::pos(K)], w);
+            });
+            fwd_twiddle_u<S, U + 1>(v, lt, twA, twB);
+        }
+    }
+    template <int S, int U> static SLMGS_DEVICE void store_scrambled_u(cf* v, int lt, cf* s, int si) {
+        if constexpr (U < E / radix<S>()) {
+            inv_store<S, U, 0>(v, lt, s, si);  // s[element K] = v[pos(K)]
+            store_scrambled_u<S, U + 1>(v, lt, s, si);
+        }
+    }
+    template <int S, int U, class TP> static SLMGS_DEVICE void inv_twiddle_u(cf* v, int lt, TP twA, TP twB) {
+        if constexpr (U < E / radix<S>()) {
+            inv_twiddle_all<S, U>(v, lt, twA, twB);
+            inv_twiddle_u<S, U + 1>(v, lt, twA, twB);
+        }
+    }
+    template <int S, int U> static SLMGS_DEVICE void inv_compute_u(cf* v) {
+        if constexpr (U < E / radix<S>()) {
+            RegFFT<radix<S>()>::template run<-1, 1>(v + U * radix<S>());
+            inv_compute_u<S, U + 1>(v);
+        }
+    }
+    template <int S, class Sy, class TP>
+    static SLMGS_DEVICE void fwd_stage_sy(cf* v, int lt, TP twA, TP twB, cf* s, int si, Sy& sy) {
+        if constexpr (S > 0) {
+            fwd_load_u<S, 0>(v, lt, s, si);
+            sy.release();
+        }
+        fwd_compute_u<S, 0>(v);
+        if constexpr (S < NS - 1) {
+            fwd_twiddle_u<S, 0>(v, lt, twA, twB);
+            sy.acquire();
+            store_scrambled_u<S, 0>(v, lt, s, si);
+        } else {
+            cf o[E];
+            unscramble_all<radix<S>(), 0>(v, o);
+            SLMGS_UNROLL
+            for (int i = 0; i < E; ++i) v[i] = o[i];
+        }
+    }
+    // (S == 0: the caller acquires before it stores the results to global memory)
+    template <int S, class Sy, class TP>
+    static SLMGS_DEVICE void inv_stage_sy(cf* v, int lt, TP twA, TP twB, cf* s, int si, Sy& sy) {
+        if constexpr (S < NS - 1) {
+            fwd_load_u<S, 0>(v, lt, s, si);
+            sy.release();
+            inv_twiddle_u<S, 0>(v, lt, twA, twB);
+        }
+        inv_compute_u<S, 0>(v);
+        if constexpr (S > 0) {
+            sy.acquire();
+            store_scrambled_u<S, 0>(v, lt, s, si);
+        } else {
+            cf o[E];
+            unscramble_all<R0, 0>(v, o);
+            SLMGS_UNROLL
+            for (int i = 0; i < E; ++i) v[i] = o[i];
         }
     }
 

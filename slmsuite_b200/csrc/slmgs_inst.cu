@@ -144,6 +144,43 @@ int SLMGS_CAT(launch_colp_, SLMGS_N)(int var, int dense, int gx, int gy, int nth
 int SLMGS_CAT(launch_colp_, SLMGS_N)(int, int, int, int, int, rt_stream, const ColArgs&) { return -1; }
 #endif
 
+// Team kernels (slmgs_teams.h): TMA-staged tiles, two compute teams per persistent block.  Lines of 2048 / 4096 points
+// (three radix stages, 16 points per thread).  `tmap` = host copy of the CUtensorMap over the row-pair interleaved field.
+// Under emulation the plain kernels run instead (same arithmetic: the team kernels call the same functions).
+#if SLMGS_N >= 2048 && SLMGS_N <= 4096
+#define SLMGS_HAVE_TEAMS 1
+#ifndef SLMGS_EMULATE
+template <int VAR> static int launch_colt_var(int dense, int gx, int gy, rt_stream s, const ColArgs& a, const void* tmap) {
+    const CUtensorMap& tm = *reinterpret_cast<const CUtensorMap*>(tmap);
+    if (dense) return launch_kernel_teams<ColKernelT<SLMGS_N, VAR, true> >(gx, gy, s, a, tm, a.pdl != 0);
+    return launch_kernel_teams<ColKernelT<SLMGS_N, VAR, false> >(gx, gy, s, a, tm, a.pdl != 0);
+}
+int SLMGS_CAT(launch_colt_, SLMGS_N)(int var, int dense, int gx, int gy, rt_stream s, const ColArgs& a, const void* tmap) {
+    switch (var) {
+        case VAR_GS: return launch_colt_var<VAR_GS>(dense, gx, gy, s, a, tmap);
+        case VAR_POW: return launch_colt_var<VAR_POW>(dense, gx, gy, s, a, tmap);
+        case VAR_POW_STORED: return launch_colt_var<VAR_POW_STORED>(dense, gx, gy, s, a, tmap);
+        default: return launch_colt_var<VAR_GENERAL>(dense, gx, gy, s, a, tmap);
+    }
+}
+int SLMGS_CAT(launch_rowt_, SLMGS_N)(int store, int dense, int gx, int gy, rt_stream s, const RowArgs& a) {
+    if (store) return launch_kernel_teams<RowKernelT<SLMGS_N, true, false> >(gx, gy, s, a, a.pdl != 0);
+    if (dense) return launch_kernel_teams<RowKernelT<SLMGS_N, false, true> >(gx, gy, s, a, a.pdl != 0);
+    return launch_kernel_teams<RowKernelT<SLMGS_N, false, false> >(gx, gy, s, a, a.pdl != 0);
+}
+#else
+int SLMGS_CAT(launch_colt_, SLMGS_N)(int var, int, int, int gy, rt_stream s, const ColArgs& a, const void*) {
+    return SLMGS_CAT(launch_col_, SLMGS_N)(COL_FUSED, var, a.W / 2, gy, 2 * Fft<SLMGS_N>::TPL, s, a);
+}
+int SLMGS_CAT(launch_rowt_, SLMGS_N)(int, int, int, int gy, rt_stream s, const RowArgs& a) {
+    return SLMGS_CAT(launch_row_, SLMGS_N)(ROW_FUSED, (a.h + 1) / 2, gy, 2 * Fft<SLMGS_N>::TPL, s, a);
+}
+#endif
+#else
+int SLMGS_CAT(launch_colt_, SLMGS_N)(int, int, int, int, rt_stream, const ColArgs&, const void*) { return -1; }
+int SLMGS_CAT(launch_rowt_, SLMGS_N)(int, int, int, int, rt_stream, const RowArgs&) { return -1; }
+#endif
+
 LaunchInfo SLMGS_CAT(launch_info_, SLMGS_N)() {
     typedef Fft<SLMGS_N> F;
     LaunchInfo i;
@@ -158,6 +195,10 @@ LaunchInfo SLMGS_CAT(launch_info_, SLMGS_N)() {
     i.p_npre = 0;
     i.p_ct = 0;
     i.p_box_rows = 0;
+    i.teams = 0;
+#ifdef SLMGS_HAVE_TEAMS
+    i.teams = 1;
+#endif
 #ifdef SLMGS_HAVE_COLP
     {
         typedef ColKernelP<SLMGS_N, VAR_GS, (16384 / F::E) / F::TPL, true> K;

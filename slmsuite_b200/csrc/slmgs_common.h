@@ -128,7 +128,7 @@ SLMGS_HD cf cmake(float re, float im) { return make_float2(re, im); }
 //     a * conj(w) = (a.x, a.y) * w.x + ( a.y, -a.x) * w.y        FMUL2 + FFMA2
 // Rounding is that of the scalar FMUL + FFMA sequence the compiler contracts the plain expression to.
 SLMGS_HD cf cadd(cf a, cf b) { return __fadd2_rn(a, b); }
-SLMGS_HD cf csub(cf a, cf b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
+SLMGS_HD cf csub(cf a, cf b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }  // FADD2 R, R, -R (the negation is an operand modifier)
 SLMGS_HD cf cmul(cf a, cf b) {
     return __ffma2_rn(make_float2(-a.y, a.x), make_float2(b.y, b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
 }

@@ -48,6 +48,13 @@ SLMGS_DEVICE void bulk_prefetch_l2(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// The two teams of a block should run about half a tile-time apart (in phase they queue their exchanges together and
+// then compete for the FMA pipe).  The offset is set once, by when team 0 requests team 1's FIRST tile: after barrier
+// number SLMGS_TEAMS_STAGGER of its own first tile (0 = as early as possible); it then persists, both teams doing
+// equal work per tile.
+#ifndef SLMGS_TEAMS_STAGGER
+#define SLMGS_TEAMS_STAGGER 0
+#endif
 template <int N, int VAR, bool DENSE> struct ColKernelT {
     typedef ColKernel<N, COL_FUSED, VAR, 2, DENSE> Base;
     typedef typename Base::F F;
@@ -133,6 +140,9 @@ template <int N, int VAR, bool DENSE> struct ColKernelT {
             mbar_init(full + 0, 1);
             mbar_init(full + 1, 1);
         }
+        // Programmatic dependent launch: everything above (twiddle rows, barriers, descriptor prefetch) overlaps the tail
+        // of the previous kernel; no access to the field or the images before it has completed and flushed.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         __syncthreads();
         if (team == 0 && n_my > 0) issue_load(a, tmap, stage, full + 0, blockIdx.x, id.by, id.tid);
         typename Base::State st;
@@ -160,22 +170,29 @@ template <int N, int VAR, bool DENSE> struct ColKernelT {
             F::template fwd_twiddle_u<0, 0>(st.v, L.lt, twA, twB);
             if (elected) bulk_wait_read0();  // this team's previous tile has left the exchange buffer
             team_bar(team);                  // ... and every thread of the team has read the staging buffer
-            if (i + 1 < n_my) {
-                issue_load(a, tmap, stage, full + (team ^ 1), q + (int)gridDim.x, id.by, id.tid);
-                if (id.tid == 32 * (NWARP - 1)) prefetch_images(a, q + (int)gridDim.x, id.by);
-            }
+            auto request_next = [&](int point) {
+                if (i + 1 < n_my && point == (i == 0 ? SLMGS_TEAMS_STAGGER : 0)) {
+                    issue_load(a, tmap, stage, full + (team ^ 1), q + (int)gridDim.x, id.by, id.tid);
+                    if (id.tid == 32 * (NWARP - 1)) prefetch_images(a, q + (int)gridDim.x, id.by);
+                }
+            };
+            request_next(0);
             F::template store_scrambled_u<0, 0>(st.v, L.lt, L.s, C);
             team_bar(team);
+            request_next(1);
             NoSync sy;
             F::template fwd_stage_sy<1>(st.v, L.lt, twA, twB, L.s, C, sy);
             team_bar(team);
+            request_next(2);
             Base::prefetch_images_head(a, L);
             F::template fwd_stage_sy<2>(st.v, L.lt, twA, twB, L.s, C, sy);
             Base::template constrain<false>(st, a, id, L);
             F::template inv_stage_sy<2>(st.v, L.lt, twA, twB, L.s, C, sy);
             team_bar(team);
+            request_next(3);
             F::template inv_stage_sy<1>(st.v, L.lt, twA, twB, L.s, C, sy);
             team_bar(team);
+            request_next(4);
             F::template inv_stage_sy<0>(st.v, L.lt, twA, twB, L.s, C, sy);
             team_bar(team);  // the exchange buffer has been read: it now takes the output tile
             cf* op = exch + sidx(id.tid >> 1, id.tid & 1);
@@ -265,11 +282,12 @@ template <int N, bool STORE, bool DENSE> struct RowKernelT {
         if (threadIdx.x == 0) {
             mbar_init(full + 0, 1);
             mbar_init(full + 1, 1);
-            if (blockIdx.x == 0) {  // (RowKernel::phase<0>: accumulator slots of the column kernel that follows)
-                if (a.zero_acc) a.zero_acc[(long long)id.by * a.zero_bs] = 0.0;
-                if (a.zero_acc2) a.zero_acc2[(long long)id.by * a.zero_bs] = 0.0;
-                if (a.win_dst) a.win_dst[id.by] = (float)(1.0 / sqrt(a.win_src[(long long)id.by * a.zero_bs]));
-            }
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // (see ColKernelT::run)
+        if (threadIdx.x == 0 && blockIdx.x == 0) {  // (RowKernel::phase<0>: accumulator slots of the column kernel that follows)
+            if (a.zero_acc) a.zero_acc[(long long)id.by * a.zero_bs] = 0.0;
+            if (a.zero_acc2) a.zero_acc2[(long long)id.by * a.zero_bs] = 0.0;
+            if (a.win_dst) a.win_dst[id.by] = (float)(1.0 / sqrt(a.win_src[(long long)id.by * a.zero_bs]));
         }
         __syncthreads();
         if (team == 0 && elected && n_my > 0) issue_load(a, stage, full + 0, blockIdx.x, id.by, id.tid);
@@ -293,19 +311,27 @@ template <int N, bool STORE, bool DENSE> struct RowKernelT {
             F::template inv_compute_u<NS - 1, 0>(st.v);
             if (elected) bulk_wait_read0();
             team_bar(team);
-            if (elected && i + 1 < n_my) issue_load(a, stage, full + (team ^ 1), q + (int)gridDim.x, id.by, id.tid);
+            auto request_next = [&](int point) {
+                if (elected && i + 1 < n_my && point == (i == 0 ? SLMGS_TEAMS_STAGGER : 0))
+                    issue_load(a, stage, full + (team ^ 1), q + (int)gridDim.x, id.by, id.tid);
+            };
+            request_next(0);
             SLMGS_PP_STAMP(team, 4);
             F::template store_scrambled_u<NS - 1, 0>(st.v, L.lt, L.s, LI);
             team_bar(team);
+            request_next(1);
             NoSync sy;
             F::template inv_stage_sy<1>(st.v, L.lt, twA, twB, L.s, LI, sy);
             team_bar(team);
+            request_next(2);
             F::template inv_stage_sy<0>(st.v, L.lt, twA, twB, L.s, LI, sy);
             Base::template project<true, STORE>(st, a, id, L);
             F::template fwd_stage_sy<0>(st.v, L.lt, twA, twB, L.s, LI, sy);
             team_bar(team);
+            request_next(3);
             F::template fwd_stage_sy<1>(st.v, L.lt, twA, twB, L.s, LI, sy);
             team_bar(team);
+            request_next(4);
             F::template fwd_stage_sy<2>(st.v, L.lt, twA, twB, L.s, LI, sy);
             team_bar(team);
             SLMGS_UNROLL
@@ -332,13 +358,11 @@ __global__ void __launch_bounds__(2 * K::T, 1) slmgs_kernel_teams_col(const type
     extern __shared__ __align__(128) unsigned char slmgs_smem_teams[];
     if (threadIdx.x == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     K::run(a, &tmap, slmgs_smem_teams);
 }
 template <class K> __global__ void __launch_bounds__(2 * K::T, 1) slmgs_kernel_teams_row(const typename K::Args a) {
     extern __shared__ __align__(128) unsigned char slmgs_smem_teams[];
     asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     K::run(a, nullptr, slmgs_smem_teams);
 }
 

@@ -576,6 +576,11 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
         c->teams_col = on && c->icol.teams && c->col_threads == 2 * c->icol.tpl && (c->h % 2) == 0 && (c->i0 % 2) == 0 &&
                        setup_teams_col(c);
         c->teams_row = on && c->irow.teams && (c->h % 2) == 0 && (c->i0 % 2) == 0 && c->H >= 32;
+        // a persistent block pays for its prologue (twiddle rows into shared memory, the first tile's latency): only worth it
+        // with a few work items per team (configs[1] has 576 row pairs for 296 teams: the plain row kernel stays, 31 vs 33 us)
+        const long long teams_gpu = 2LL * c->sms;
+        if ((long long)(c->h / 2) * c->B < 4 * teams_gpu) c->teams_row = false;
+        if ((long long)(c->W / 2) * c->B < 4 * teams_gpu) c->teams_col = false;
     }
     CR(rt_check(c, rt_sync(c->stream), "sync"));
 #undef CR

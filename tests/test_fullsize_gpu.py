@@ -366,3 +366,31 @@ def test_config4_batch_member_vs_oracle(cuda):
         assert rel_rmse(amp[b], o.amp_ff) <= 1e-5
         nf = np.abs(o.nearfield)
         assert _phase_rms(ph[b], o.phase, nf > 1e-4 * nf.max()) <= 2e-5
+
+
+@pytest.mark.parametrize("case", ["dense_gs", "dense_kim", "padded_kim", "padded_gs"])
+def test_team_kernels_bit_identical_to_plain_kernels(cuda, case, monkeypatch):
+    """The TMA / two-team kernels of the dense-far-field loop (csrc/slmgs_teams.h) call the same arithmetic as the
+    plain fused kernels: SLMGS_TEAMS=1 and SLMGS_TEAMS=0 must agree BIT FOR BIT (phase, weights, far-field
+    amplitude) on the 4096^2 configurations, dense and zero padded, GS and WGS-Kim across the phase-fixing iteration."""
+    from slmsuite_b200 import Hologram
+
+    rng = np.random.default_rng(11)
+    shape = (4096, 4096)
+    slm = shape if case.startswith("dense") else (1152, 1920)
+    target = rng.random(shape, dtype=np.float32)
+    phase = rng.uniform(-np.pi, np.pi, slm).astype(np.float32)
+    method = "GS" if "gs" in case else "WGS-Kim"
+    kw = dict(method=method, maxiter=6, verbose=False)
+    if method == "WGS-Kim":
+        kw["fix_phase_iteration"] = 3
+    out = []
+    for teams in ("1", "0"):
+        monkeypatch.setenv("SLMGS_TEAMS", teams)
+        monkeypatch.setenv("SLMGS_SPARSE", "0")
+        h = Hologram(target, phase=phase, slm_shape=slm)
+        h.optimize(**kw)
+        out.append((h.phase.copy(), h.weights.copy(), h.amp_ff.copy()))
+        del h
+    for a, b in zip(*out):
+        assert a.tobytes() == b.tobytes()

@@ -46,6 +46,8 @@ typedef ColKernel<NN, COL_FUSED, VAR_GS, 2, true> KCol;
 typedef RowKernel<NN, ROW_FUSED, false, false, 2, true> KRow;
 typedef ColKernelT<NN, VAR_GS, true> KColT;
 typedef RowKernelT<NN, false, true> KRowT;
+typedef ColKernel<NN, COL_FUSED, VAR_POW, 2, true> KColPow;
+typedef ColKernelT<NN, VAR_POW, true> KColPowT;
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -64,9 +66,6 @@ static CUtensorMap make_tmap(cf* fld, int H, int W) {
     if (r != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled failed: %d\n", (int)r); exit(1); }
     return tm;
 }
-#ifdef WITH_POW
-typedef ColKernel<NN, COL_FUSED, VAR_POW, 2, true> KColPow;
-#endif
 
 template <class Fn> static float time_ms(int reps, Fn fn) {
     cudaEvent_t e0, e1;
@@ -228,6 +227,19 @@ int main(int argc, char** argv) {
         CK(launch_kernel<KCol>(W / 2, 1, 512, col_smem, 0, ca, true));
         CK(launch_kernel<KRow>(H / 2, 1, 512, row_smem, 0, ra, true));
     });
+    {   // WGS (power-law update): weights read + written, target read -- timing only (the weights evolve)
+        float* target;
+        CK(cudaMalloc(&target, P * sizeof(float)));
+        CK(cudaMemcpy(target, weights, P * sizeof(float), cudaMemcpyDeviceToDevice));
+        ColArgs cw = ca;
+        cw.target = target;
+        cw.wgs_update = 1; cw.wgs.method = METHOD_KIM; cw.wgs.p = 0.8f; cw.w_out_slot = 0; cw.wgs.inv_fnorm = 1.0f;
+        const double powB = 28.0 * P;
+        t = time_ms(reps, [&]() { CK(launch_kernel<KColPow>(W / 2, 1, 512, col_smem, 0, cw)); });
+        printf("col WGS plain     : %8.2f us  %7.1f GB/s\n", t * 1e3, powB / t * 1e-6);
+        t = time_ms(reps, [&]() { CK(launch_kernel_teams<KColPowT>(pgx, 1, 0, cw, tmap1)); });
+        printf("col WGS TMA teams : %8.2f us  %7.1f GB/s\n", t * 1e3, powB / t * 1e-6);
+    }
     printf("iteration plain (PDL)     : %8.2f us -> %6.0f it/s\n", t * 1e3, 1e3 / t);
     t = time_ms(reps, [&]() {
         CK(launch_kernel_pp<KCol>(pgx, 1, col_smem, 0, ca, true));

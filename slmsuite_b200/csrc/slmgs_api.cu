@@ -268,12 +268,13 @@ static int scratch_reserve(slmgs_ctx* c, size_t bytes, void** out) {
 }
 
 static void make_twiddles(int n, std::vector<cf>& a, std::vector<cf>& b) {
-    // twA[k0*M1 + j] = exp(-2 pi i j k0 / N), twB[k1*R2 + n2] = exp(-2 pi i n2 k1 / M1) for the plan of this size
+    // twA[k0*M1 + j] = exp(-2 pi i j k0 / N), twB[k1*M2 + r] = exp(-2 pi i r k1 / M1) for the plan of this size
+    // (M1 = R1 R2 R3, M2 = R2 R3), and for four-stage plans, behind twB: twC[k2*R3 + n3] = exp(-2 pi i n3 k2 / M2)
     const LaunchInfo li = size_info(n);
-    const int r0 = li.r0, r1 = li.r1, r2 = li.r2;
-    const int m1 = r1 * r2;
+    const int r0 = li.r0, r1 = li.r1, r2 = li.r2, r3 = li.r3;
+    const int m1 = r1 * r2 * r3, m2 = r2 * r3;
     a.resize(n);
-    b.resize(m1);
+    b.resize(m1 + (r3 > 1 ? m2 : 0));
     const double tau = 6.283185307179586476925286766559;
     for (int k0 = 0; k0 < r0; ++k0)
         for (int j = 0; j < m1; ++j) {
@@ -281,10 +282,16 @@ static void make_twiddles(int n, std::vector<cf>& a, std::vector<cf>& b) {
             a[k0 * m1 + j] = make_float2((float)cos(ang), (float)sin(ang));
         }
     for (int k1 = 0; k1 < r1; ++k1)
-        for (int n2 = 0; n2 < r2; ++n2) {
-            const double ang = -tau * (double)((n2 * k1) % m1) / (double)m1;
-            b[k1 * r2 + n2] = make_float2((float)cos(ang), (float)sin(ang));
+        for (int r = 0; r < m2; ++r) {
+            const double ang = -tau * (double)((r * k1) % m1) / (double)m1;
+            b[k1 * m2 + r] = make_float2((float)cos(ang), (float)sin(ang));
         }
+    if (r3 > 1)
+        for (int k2 = 0; k2 < r2; ++k2)
+            for (int n3 = 0; n3 < r3; ++n3) {
+                const double ang = -tau * (double)((n3 * k2) % m2) / (double)m2;
+                b[m1 + k2 * r3 + n3] = make_float2((float)cos(ang), (float)sin(ang));
+            }
 }
 
 static int env_int(const char* name, int dflt) {
@@ -324,22 +331,25 @@ static void choose_geometry(slmgs_ctx* c) {
         // two resident blocks per SM (<= 512 threads, <= ~70 KB shared memory each) overlap one block's
         // global-memory phases with the other's butterflies: measured 108 vs 124 us at 4096^2 on B200
         int nt = li.maxt > 512 && li.tpl <= 512 ? 512 : li.maxt;
-        while (nt > lo && (size_t)(nt / li.tpl) * li.padn * sizeof(cf) > 113 * 1024) nt >>= 1;  // N = 8192: one line per block
+        // (8192-point rows: a line is 64 KB, two of them fill an SM -- kept, one block per SM, because the row-pair
+        // interleaved layout needs two lines per block and pays on the column side: configs[4] 18.9 -> 16.6 ms per 10 it)
+        const bool pair8192 = c->W == 8192 && c->h >= 2 && env_int("SLMGS_PAIRS8192", 1) != 0;
+        while (nt > lo && (size_t)(nt / li.tpl) * li.padn * sizeof(cf) > 113 * 1024 && !(pair8192 && nt / li.tpl == 2)) nt >>= 1;
         while (nt > lo) {
             const int lines = nt / li.tpl;
             const long long blocks = (long long)((c->h + lines - 1) / lines) * c->B;
             if (blocks >= want) break;
             nt >>= 1;
         }
+        if (pair8192 && li.maxt / li.tpl >= 2) nt = 2 * li.tpl;  // (also with the four-stage plan: 512 threads per line)
         int o = env_int("SLMGS_ROW_THREADS", 0);
         if (o >= lo && o <= li.maxt && (o & (o - 1)) == 0) nt = o;
         c->row_threads = nt;
         const int lines = nt / li.tpl;
         c->row_gx = (c->h + lines - 1) / lines;
-        // row-pair interleaved field layout: two lines per warp in the row kernels, so an even number of lines per
-        // block; not built for 8192-point rows (one line per block)
+        // row-pair interleaved field layout: two lines per warp in the row kernels, so an even number of lines per block
         // (H >= 32: the column kernel steps through rows b + (H/R0) m and relies on an even H/R0)
-        c->pairs = env_int("SLMGS_PAIRS", 1) != 0 && c->W < 8192 && lines % 2 == 0 && c->H >= 32;
+        c->pairs = env_int("SLMGS_PAIRS", 1) != 0 && lines % 2 == 0 && c->H >= 32;
     }
     // columns: C = threads / tpl columns per block; keep >= 4 columns (one 32-byte sector per row)
     {

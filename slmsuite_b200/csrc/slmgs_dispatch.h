@@ -16,7 +16,7 @@ struct LaunchInfo {
     int maxt;    // max threads per block
     int padn;    // padded line length (complex elements)
     int ns;      // number of radix stages
-    int r0, r1, r2;  // stage radices of the plan (twiddle table layout)
+    int r0, r1, r2, r3;  // stage radices of the plan (twiddle table layout); r3 = 1 for three-stage plans
     int p_npre;      // persistent TMA column kernel (ColKernelP): staged boxes per tile, 0 = not built for this size
     int p_ct;        // ... its tile width (columns) at maxt threads
     int p_box_rows;  // ... rows per box

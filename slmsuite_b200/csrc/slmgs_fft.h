@@ -23,6 +23,11 @@
 // forward -> pointwise -> inverse (column kernel) and inverse -> pointwise -> forward (row
 // kernel) chain without any data movement in between.
 //
+// Four stages (N = 8192 = 2*16*16*16): one more digit, n = ((n0 R1 + n1) R2 + n2) R3 + n3, k = k0 + R0 (k1 + R1 (k2 + R2 k3)):
+//   stage C becomes a middle stage (butterfly b = (k0 + R0*k1)*R3 + n3, elements along n2/k2) and stage D
+//   (radix R3, butterfly b = k0 + R0*k1 + R0*R1*k2) the last one; with R3 = 1 every formula below reduces to the
+//   three-stage one.  A third table follows twB in the same allocation: twC[k2*R3 + n3] = exp(-2 pi i n3 k2 / (R2 R3)).
+//
 // Twiddles come from two small host-computed tables (double precision, rounded once):
 //   twA[k0*M1 + j] = exp(-2 pi i j k0 / N)   (N entries, indexed by the line index itself)
 //   twB[k1*R2 + n2] = exp(-2 pi i n2 k1 / M1) (M1 entries)
@@ -47,10 +52,11 @@ struct SmemTw {
 template <int N> struct Plan;
 // E: points per thread; R0,R1,R2: stage radices (smallest first so the two big stages keep 16 consecutive
 // lanes on consecutive addresses); P2: pad of the k0 stride (see "Shared memory layout" below).
-#define SLMGS_PLAN(N_, E_, A_, B_, C_, P2_)                                     \
-    template <> struct Plan<N_> {                                               \
-        static constexpr int E = E_, R0 = A_, R1 = B_, R2 = C_, P2 = P2_;       \
+#define SLMGS_PLAN4(N_, E_, A_, B_, C_, D_, P2_)                                         \
+    template <> struct Plan<N_> {                                                        \
+        static constexpr int E = E_, R0 = A_, R1 = B_, R2 = C_, R3 = D_, P2 = P2_;       \
     };
+#define SLMGS_PLAN(N_, E_, A_, B_, C_, P2_) SLMGS_PLAN4(N_, E_, A_, B_, C_, 1, P2_)
 SLMGS_PLAN(16, 16, 16, 1, 1, 0)
 SLMGS_PLAN(32, 16, 2, 16, 1, 1)
 SLMGS_PLAN(64, 16, 4, 16, 1, 1)
@@ -63,43 +69,58 @@ SLMGS_PLAN(2048, 16, 8, 16, 16, 2)
 #define SLMGS_E4096 16
 #endif
 SLMGS_PLAN(4096, SLMGS_E4096, 16, 16, 16, 1)
+// 8192 points: 32 points per thread, three stages (128 registers; the hot kernels spill a few registers).  The
+// four-stage plan 2*16*16*16 (-DSLMGS_8192_4STAGE: 16 points per thread, 64 registers, no spills in the hot kernels) was
+// measured SLOWER on B200 (configs[4], 10 iterations: 17.9 vs 16.6 ms): its extra exchange and twiddle layer cost more than
+// the spills and the halved occupancy of this one.
+#ifdef SLMGS_8192_4STAGE
+SLMGS_PLAN4(8192, 16, 2, 16, 16, 16, 8)
+#else
 SLMGS_PLAN(8192, 32, 32, 16, 16, 1)
+#endif
+#undef SLMGS_PLAN4
 #undef SLMGS_PLAN
 
 template <int N> struct Fft {
     typedef Plan<N> P;
-    static constexpr int E = P::E, R0 = P::R0, R1 = P::R1, R2 = P::R2;
-    static constexpr int NS = 1 + (R1 > 1) + (R2 > 1);
-    static constexpr int M1 = R1 * R2;
+    static constexpr int E = P::E, R0 = P::R0, R1 = P::R1, R2 = P::R2, R3 = P::R3;
+    static constexpr int NS = 1 + (R1 > 1) + (R2 > 1) + (R3 > 1);
+    static constexpr int M1 = R1 * R2 * R3;  // points behind the first digit
+    static constexpr int M2 = R2 * R3;       // ... behind the second
     static constexpr int TPL = N / E;
-    static_assert(R0 * R1 * R2 == N, "bad plan");
-    // Shared memory layout.  A line index i = k0*M1 + x*R2 + y (k0 < R0, x < R1, y < R2) is stored at
-    //     k0*T2 + x*T1 + y,   T1 = R2 + (R2 > 1),   T2 = R1*T1 + P2
-    // i.e. plain digit strides with small pads.  Element m of a butterfly is then always at
+    static_assert(R0 * R1 * R2 * R3 == N, "bad plan");
+    static_assert(R3 == 1 || (R1 > 1 && R2 > 1), "a fourth stage needs the other three");
+    // Shared memory layout.  A line index i = ((d0 R1 + d1) R2 + d2) R3 + d3 is stored at
+    //     d0*T2 + d1*T1 + d2*T0 + d3,   T0 = R3 + (R3 > 1),   T1 = R2*T0 + (R2 > 1),   T2 = R1*T1 + P2
+    // i.e. plain digit strides with small pads (three stages: R3 = 1, T0 = 1).  Element m of a butterfly is then always at
     // base(b) + m*const, so the 16 shared-memory accesses of a stage use one address register with
     // compile-time offsets.  Pads are chosen so that within every half-warp (16 lanes, 8-byte accesses)
-    // the three access patterns hit 16 distinct bank pairs:
-    //   lanes along y (stages A, B): consecutive;    lanes along k0 (stage C): stride T2 = P2 (mod 16),
-    //   P2*k0 + k1 distinct for the R0 x 16/R0 lanes of a half-warp.
-    static constexpr int T1 = R2 + (R2 > 1 ? 1 : 0);
+    // the access patterns hit 16 distinct bank pairs:
+    //   lanes along the last digit (all stages but the last): consecutive;    last stage: lanes along d0 (stride T2 = P2
+    //   mod 16) and d1 (stride T1 = 1 mod 16): P2*d0 + d1 distinct for the R0 x 16/R0 lanes of a half-warp.
+    static constexpr int T0 = R3 + (R3 > 1 ? 1 : 0);
+    static constexpr int T1 = R2 * T0 + (R2 > 1 ? 1 : 0);
     static constexpr int T2 = R1 * T1 + P::P2;
     static constexpr int PADN = R0 * T2 + 1;
 
-    template <int S> static constexpr int radix() { return S == 0 ? R0 : S == 1 ? R1 : R2; }
+    template <int S> static constexpr int radix() { return S == 0 ? R0 : S == 1 ? R1 : S == 2 ? R2 : R3; }
     static constexpr int last_radix() { return radix<NS - 1>(); }
 
     // shared-memory position of element 0 of butterfly b at stage S, and the stride between elements
+    //   S = 0: b = (d1, d2, d3);  S = 1: b = (d0, d2, d3);  S = 2: b = ((d0 + R0 d1), d3);  S = 3: b = d0 + R0 (d1 + R1 d2)
     template <int S> static SLMGS_HD int sbase(int b) {
-        if (S == 0) return (b / R2) * T1 + (b % R2);
-        if (S == 1) return (b / R2) * T2 + (b % R2);
-        return (b % R0) * T2 + (b / R0) * T1;
+        if (S == 0) return (b / M2) * T1 + ((b / R3) % R2) * T0 + (b % R3);
+        if (S == 1) return (b / M2) * T2 + ((b / R3) % R2) * T0 + (b % R3);
+        if (S == 2) return ((b / R3) % R0) * T2 + ((b / R3) / R0) * T1 + (b % R3);
+        return (b % R0) * T2 + ((b / R0) % R1) * T1 + (b / (R0 * R1)) * T0;
     }
-    template <int S> static constexpr int sstride() { return S == 0 ? T2 : S == 1 ? T1 : 1; }
+    template <int S> static constexpr int sstride() { return S == 0 ? T2 : S == 1 ? T1 : S == 2 ? T0 : 1; }
     // twiddle applied after forward stage S (S < NS-1) to output m of butterfly b
     template <int S> static SLMGS_DEVICE cf twiddle(const cf* SLMGS_RESTRICT twA, const cf* SLMGS_RESTRICT twB, int b,
                                                    int m) {
         if (S == 0) return __ldg(twA + m * M1 + b);
-        return __ldg(twB + m * R2 + (b % R2));
+        if (S == 1) return __ldg(twB + m * M2 + (b % M2));
+        return __ldg(twB + M1 + m * R3 + (b % R3));  // third table, stored behind the second
     }
     // The same from a compact copy of the tables in shared memory (persistent kernels, slmgs_teams.h): with
     // SLMGS_TW_PRODUCTS only the rows m = 1, 2, 4, 8 of either table are ever read; row m is stored at log2(m).
@@ -107,6 +128,7 @@ template <int N> struct Fft {
     static constexpr int TWS_A = TWS_ROWS * M1, TWS_B = TWS_ROWS * R2;  // entries of the compact tables
     static SLMGS_HD int tws_row(int m) { return m == 1 ? 0 : m == 2 ? 1 : m == 4 ? 2 : 3; }
     template <int S> static SLMGS_DEVICE cf twiddle(SmemTw twA, SmemTw twB, int b, int m) {
+        static_assert(R3 == 1, "compact shared-memory tables: three-stage plans");
         if (S == 0) return twA.p[tws_row(m) * M1 + b];
         return twB.p[tws_row(m) * R2 + (b % R2)];
     }

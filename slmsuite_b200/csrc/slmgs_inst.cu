@@ -55,14 +55,10 @@ template <int LI> static int launch_row_li(int mode, int gx, int gy, int nthread
 
 // the row-pair interleaved field layout needs an even number of lines per block (two lines share every warp)
 int SLMGS_CAT(launch_row_, SLMGS_N)(int mode, int gx, int gy, int nthreads, rt_stream s, const RowArgs& a) {
-#if SLMGS_N < 8192
     if (a.pairs) {
         if ((nthreads / Fft<SLMGS_N>::TPL) % 2 != 0) return -1;
         return launch_row_li<2>(mode, gx, gy, nthreads, s, a);
     }
-#else
-    if (a.pairs) return -1;
-#endif
     return launch_row_li<1>(mode, gx, gy, nthreads, s, a);
 }
 
@@ -119,7 +115,7 @@ int SLMGS_CAT(launch_col_, SLMGS_N)(int mode, int var, int gx, int gy, int nthre
 }
 
 // persistent fused column kernel with TMA-staged tiles: long columns only, full-size blocks
-#if SLMGS_N >= 2048
+#if SLMGS_N >= 2048 && SLMGS_N <= 4096
 #define SLMGS_HAVE_COLP 1
 template <int VAR> static int launch_colp_var(int dense, int gx, int gy, int nthreads, rt_stream s, const ColArgs& a) {
     typedef Fft<SLMGS_N> F;
@@ -192,6 +188,7 @@ LaunchInfo SLMGS_CAT(launch_info_, SLMGS_N)() {
     i.r0 = F::R0;
     i.r1 = F::R1;
     i.r2 = F::R2;
+    i.r3 = F::R3;
     i.p_npre = 0;
     i.p_ct = 0;
     i.p_box_rows = 0;

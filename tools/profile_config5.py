@@ -9,7 +9,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from slmsuite_b200 import SpotHologram, _lib  # noqa: E402
 
-lib = _lib.use_library(_lib.DEFAULT_LIBRARY)
+lib = _lib.use_library(os.environ.get("SLMGS_LIB") or _lib.DEFAULT_LIBRARY)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 rng = np.random.default_rng(0)
 v = np.random.default_rng(5).uniform(64, n - 64, (2, 10000))

@@ -188,6 +188,8 @@ struct slmgs_ctx {
     bool use_pdl;
     bool prefetch;
     bool pairs;                // fld is stored row-pair interleaved (slmgs_kernels.h, RowArgs)
+    bool populate_shortcut;    // slmgs_run: skip the row pass of _populate_results after a dense run (see run_sequence)
+    bool weights_pristine;     // weights == nan_to_num(target) since the last slmgs_reset_weights: the next reset is a no-op
     // CUDA graphs of whole slmgs_run launch sequences (small fields are launch bound): see slmgs_run
     int launch_mode;           // 0 = launch, 1 = dry run: fold every kernel's arguments into `hash` instead
     unsigned long long hash;
@@ -524,6 +526,8 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
     c->graph_clock = 0;
 #endif
     c->teams_col = c->teams_row = false;
+    c->weights_pristine = false;
+    c->populate_shortcut = env_int("SLMGS_POPULATE_REBUILD", 0) == 0;
     c->tb_pairs = c->tb_n = c->tb_lo = c->tb_hi0 = 0;
     c->colp = false;
     c->colp_dense = false;
@@ -664,6 +668,7 @@ template <int OP> static int launch_elem(slmgs_ctx* c, const ElemArgs& a, int ba
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     c->launches++;
+    if (a.dst == (void*)c->weights) c->weights_pristine = false;
     return rt_check(c, launch_kernel<ElemKernel<OP>>((int)blocks, batch, 256, 0, c->stream, a), "element-wise launch");
 }
 static int zero_slot(slmgs_ctx* c, int slot, int count = 1) {
@@ -777,6 +782,7 @@ extern "C" int slmgs_set_target(slmgs_ctx* c, const float* target, int shared) {
     if (!target) return fail(c, SLMGS_ERR_INVALID, "target is NULL");
     c->target_shared = shared ? 1 : 0;
     c->tiles_dirty = true;
+    c->weights_pristine = false;
     return upload_rolled(c, target, c->target, shared ? 1 : c->B);
 }
 extern "C" int slmgs_get_target(slmgs_ctx* c, float* target) {
@@ -787,6 +793,8 @@ extern "C" int slmgs_get_target(slmgs_ctx* c, float* target) {
 extern "C" int slmgs_reset_weights(slmgs_ctx* c) {
     CHECK_CTX(c);
     const long long P = (long long)c->H * c->W;
+    // weights untouched since the last reset (GS never updates them): nothing to copy, the tile flags are current
+    if (c->weights_pristine && c->w_pending < 0 && !c->zero_w && !c->tiles_dirty) return SLMGS_OK;
     ElemArgs a = elem_args(c, c->target, c->weights, P);
     a.src_bs = c->target_shared ? 0 : P;
     c->w_pending = -1;
@@ -805,13 +813,16 @@ extern "C" int slmgs_reset_weights(slmgs_ctx* c) {
         c->tiles_dirty = true;
     }
     if (c->zero_w) RT(c, rt_memset(c->zero_w, 0, (size_t)c->B * P * sizeof(cf), c->stream));  // zero_weights *= 0, :609-610
-    return launch_elem<EW_FILL_NAN0>(c, a, c->B);
+    const int e = launch_elem<EW_FILL_NAN0>(c, a, c->B);
+    c->weights_pristine = e == SLMGS_OK;
+    return e;
 }
 extern "C" int slmgs_set_weights(slmgs_ctx* c, const float* weights) {
     CHECK_CTX(c);
     if (!weights) return fail(c, SLMGS_ERR_INVALID, "weights is NULL");
     c->w_pending = -1;
     c->tiles_dirty = true;
+    c->weights_pristine = false;
     return upload_rolled(c, weights, c->weights, c->B);
 }
 extern "C" int slmgs_get_weights(slmgs_ctx* c, float* weights) {
@@ -994,6 +1005,7 @@ static int run_row(slmgs_ctx* c, int mode, const RowArgs& a) {
 }
 static int run_col(slmgs_ctx* c, int mode, const ColArgs& a) {
     c->launches++;
+    if (a.wgs_update || a.zero_w) c->weights_pristine = false;
     if (c->launch_mode == 1) {
         const int g[6] = {16 + mode, a.tiles ? c->n_active : c->col_gx, c->B, c->col_threads, c->colp ? 1 : 0, c->sms};
         hash_mix(c, g, sizeof g);
@@ -1194,7 +1206,7 @@ extern "C" int slmgs_sparse_info(const slmgs_ctx* c, int* out3) {
 
 static int run_prepare(slmgs_ctx* c, const slmgs_params* params, int n_iter);
 static int run_body(slmgs_ctx* c, const slmgs_params* params, int n_iter);
-static int populate_body(slmgs_ctx* c);
+static int populate_body(slmgs_ctx* c, bool fld_ready = false);
 
 // The launch sequence of a whole run (first row pass, n_iter x (column kernel, row kernel) [+ pre-passes],
 // _populate_results) only depends on host state.  Small fields are launch bound (512^2: ~7 us of host time per
@@ -1223,7 +1235,11 @@ static int run_sequence(slmgs_ctx* c, const slmgs_params* params, int n_iter, in
     const bool sp = c->sparse_now;
     int e = run_body(c, params, n_iter);
     c->sparse_now = false;
-    if (!e && populate) e = populate_body(c);
+    // A dense run ends with the fused row kernel, whose forward half has just written the row spectrum of the final near
+    // field (amp z/|z|, z = the field whose angle was stored as the phase): _populate_results only needs the column pass.
+    // (A sparse run stored the active column tiles only, and the stored-phase rebuild is bit-faithful to the reference's
+    // exp(i phase): SLMGS_POPULATE_REBUILD=1 keeps it.)
+    if (!e && populate) e = populate_body(c, n_iter > 0 && !sp && c->populate_shortcut);
     c->sparse_now = sp;
     return e;
 }
@@ -1427,10 +1443,10 @@ extern "C" int slmgs_forward(slmgs_ctx* c) {
     return SLMGS_OK;
 }
 
-static int populate_body(slmgs_ctx* c) {
+static int populate_body(slmgs_ctx* c, bool fld_ready) {
     // after a fused run `fld` already holds the row transform of the new near field only if the last
-    // kernel was ROW_FUSED; rebuilding from the stored phase is always valid and costs one row pass.
-    return forward_impl(c, c->farfield ? 1 : 0, 1, 1, true);
+    // kernel was a dense ROW_FUSED; rebuilding from the stored phase is always valid and costs one row pass.
+    return forward_impl(c, c->farfield ? 1 : 0, 1, 1, !fld_ready);
 }
 extern "C" int slmgs_populate(slmgs_ctx* c) {
     CHECK_CTX(c);
@@ -1603,6 +1619,7 @@ static int update_weights_spot_impl(slmgs_ctx* c, const slmgs_params* p, int wid
     e = rt_check(c, launch_kernel<SpotGatherKernel>((c->n_spots + 255) / 256, c->B, 256, 0, c->stream, a), "spot gather launch");
     if (e) return e;
     c->launches++;
+    c->weights_pristine = false;
     return rt_check(c, launch_kernel<SpotUpdateKernel>(1, c->B, 1024, (1024 + 8) * sizeof(double), c->stream, a), "spot update launch");
 }
 

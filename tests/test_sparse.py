@@ -15,6 +15,16 @@ from oracle import gs_oracle
 
 
 @pytest.fixture(autouse=True)
+def _rebuild_populate(monkeypatch):
+    """These tests compare a sparse run with a dense run BIT FOR BIT.  A sparse run always ends with
+    `_populate_results` rebuilt from the stored phase (its row kernel only stored the active column tiles); a dense
+    run normally skips that row pass (the last fused row kernel has already written the row spectrum of the final
+    near field, equal to the rebuilt one within float rounding, ~1e-7).  SLMGS_POPULATE_REBUILD=1 makes the dense
+    run rebuild too, so that the loop itself is what is compared."""
+    monkeypatch.setenv("SLMGS_POPULATE_REBUILD", "1")
+
+
+@pytest.fixture(autouse=True)
 def _narrow_tiles(monkeypatch):
     """Four-column tiles on both backends (the emulation pretends to have 4 SMs and would otherwise pick tiles so
     wide that the small test problems have fewer than eight of them)."""

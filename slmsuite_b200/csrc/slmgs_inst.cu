@@ -115,7 +115,8 @@ int SLMGS_CAT(launch_col_, SLMGS_N)(int mode, int var, int gx, int gy, int nthre
 }
 
 // persistent fused column kernel with TMA-staged tiles: long columns only, full-size blocks
-#if SLMGS_N >= 2048 && SLMGS_N <= 4096
+// (superseded by the team kernels below; only built with -DSLMGS_WITH_COLP, for A/B measurements)
+#if SLMGS_N >= 2048 && SLMGS_N <= 4096 && defined(SLMGS_WITH_COLP)
 #define SLMGS_HAVE_COLP 1
 template <int VAR> static int launch_colp_var(int dense, int gx, int gy, int nthreads, rt_stream s, const ColArgs& a) {
     typedef Fft<SLMGS_N> F;

@@ -394,3 +394,25 @@ def test_team_kernels_bit_identical_to_plain_kernels(cuda, case, monkeypatch):
         del h
     for a, b in zip(*out):
         assert a.tobytes() == b.tobytes()
+
+
+@pytest.mark.parametrize("shape,batch", [((2048, 2048), 3), ((4096, 4096), 2), ((2048, 4096), 2), ((4096, 2048), 2)])
+def test_team_kernels_batch_bit_identical(cuda, shape, batch, monkeypatch):
+    """Batched contexts (blockIdx.y = hologram, the persistent blocks of a team kernel are shared by the batch) and
+    rectangular 2048 / 4096 shapes (team row kernel at 2048-point rows, team column kernel only at 4096-point columns):
+    SLMGS_TEAMS=1 and SLMGS_TEAMS=0 agree bit for bit."""
+    from slmsuite_b200 import HologramBatch
+
+    rng = np.random.default_rng(21)
+    targets = rng.random((batch,) + shape, dtype=np.float32)
+    phases = rng.uniform(-np.pi, np.pi, (batch,) + shape).astype(np.float32)
+    out = []
+    for teams in ("1", "0"):
+        monkeypatch.setenv("SLMGS_TEAMS", teams)
+        monkeypatch.setenv("SLMGS_SPARSE", "0")
+        hb = HologramBatch(targets, phase=phases)
+        hb.optimize("WGS-Leonardo", maxiter=4, verbose=False)
+        out.append((hb.phase.copy(), hb.amp_ff.copy()))
+        del hb
+    for a, b in zip(*out):
+        assert a.tobytes() == b.tobytes()

@@ -99,6 +99,12 @@ static int launch_rowt(int n, int store, int dense, int gx, int gy, rt_stream s,
 #undef X
     return -1;
 }
+static int launch_loop(int n, int li, int gx, int gy, int nt, rt_stream s, const LoopArgs& a, int query) {
+#define X(N_) if (n == N_) return launch_loop_##N_(li, gx, gy, nt, s, a, query);
+    SLMGS_FOR_SIZES(X)
+#undef X
+    return query ? 0 : -1;
+}
 static int launch_colp(int n, int var, int dense, int gx, int gy, int nt, rt_stream s, const ColArgs& a) {
 #define X(N_) if (n == N_) return launch_colp_##N_(var, dense, gx, gy, nt, s, a);
     SLMGS_FOR_SIZES(X)
@@ -188,6 +194,10 @@ struct slmgs_ctx {
     bool use_pdl;
     bool prefetch;
     bool pairs;                // fld is stored row-pair interleaved (slmgs_kernels.h, RowArgs)
+    // the whole GS loop of a small square field in one cooperative kernel (slmgs_loop.h)
+    unsigned* gbar;            // grid barrier counter (device, never reset)
+    unsigned gbar_epoch;       // its value once every launch issued so far has finished
+    int loop_bps;              // resident blocks per SM of the loop kernel at this geometry (-1 = not asked yet)
     bool populate_shortcut;    // slmgs_run: skip the row pass of _populate_results after a dense run (see run_sequence)
     bool weights_pristine;     // weights == nan_to_num(target) since the last slmgs_reset_weights: the next reset is a no-op
     // CUDA graphs of whole slmgs_run launch sequences (small fields are launch bound): see slmgs_run
@@ -527,6 +537,9 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
 #endif
     c->teams_col = c->teams_row = false;
     c->weights_pristine = false;
+    c->gbar = nullptr;
+    c->gbar_epoch = 0;
+    c->loop_bps = -1;
     c->populate_shortcut = env_int("SLMGS_POPULATE_REBUILD", 0) == 0;
     c->tb_pairs = c->tb_n = c->tb_lo = c->tb_hi0 = 0;
     c->colp = false;
@@ -610,7 +623,7 @@ extern "C" int slmgs_destroy(slmgs_ctx* c) {
                     c->weights, c->phase_ff, c->amp_ff, c->twA_row, c->twB_row, c->twA_col, c->twB_col, c->acc,
                     c->partial, c->spot_x, c->spot_y, c->spot_amp, c->spot_pw, c->spot_wn, c->spot_keep, c->phase_saved, c->mp_sum, c->zero_w,
                     c->tile_flags, c->tile_list, c->tile_byte, c->tile_count, c->samp_y, c->samp_x, c->scratch, c->winf,
-                    c->tmap_dev};
+                    c->tmap_dev, c->gbar};
     for (void* p : ptrs)
         if (p) rt_free(p);
 #ifndef SLMGS_EMULATE
@@ -1327,6 +1340,77 @@ static int run_prepare(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
     return prepare_sparse(c, params, n_iter);
 }
 
+// ---- small square fields, GS: the whole loop in one cooperative kernel (slmgs_loop.h) --------------------------------
+// Geometry: every block runs one column tile (the context's tile width: it fixes the image layout) and one row group
+// with the same number of threads; all blocks must be resident at once.
+static bool loop_eligible(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
+#ifdef SLMGS_EMULATE
+    (void)c; (void)params; (void)n_iter;
+    return false;
+#else
+    if (n_iter < 2 || c->H != c->W || c->H < 256 || c->H > 1024 || c->sparse_now || c->profiling || c->launch_mode != 0 ||
+        c->w_pending >= 0 || c->prop || env_int("SLMGS_LOOP", 1) == 0)
+        return false;
+    for (int i = 0; i < n_iter; ++i) {
+        const slmgs_params* p = params + i;
+        if (p->update_weights || p->mraf || p->phase_mode != SLMGS_PHASE_COMPUTE) return false;
+    }
+    const int nt = c->col_threads;
+    const int lines = nt / c->irow.tpl;
+    if (lines < 1 || (c->pairs && (lines % 2))) return false;
+    const int col_items = c->W / (nt / c->icol.tpl), row_items = (c->h + lines - 1) / lines;
+    const int gx = col_items > row_items ? col_items : row_items;
+    if (c->loop_bps < 0) {
+        LoopArgs dummy;
+        memset(&dummy, 0, sizeof dummy);
+        c->loop_bps = launch_loop(c->H, c->pairs ? 2 : 1, gx, c->B, nt, c->stream, dummy, 1);
+    }
+    if ((long long)gx * c->B > (long long)c->loop_bps * c->sms) return false;
+    if (!c->gbar) {
+        if (dev_alloc(c, &c->gbar, 1)) return false;
+        if (rt_memset(c->gbar, 0, sizeof(unsigned), c->stream)) return false;
+        c->gbar_epoch = 0;
+    }
+    return true;
+#endif
+}
+static int run_loop(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
+#ifdef SLMGS_EMULATE
+    (void)c; (void)params; (void)n_iter;
+    return SLMGS_ERR_STATE;
+#else
+    const int nt = c->col_threads;
+    const int lines = nt / c->irow.tpl;
+    LoopArgs la;
+    memset(&la, 0, sizeof la);
+    la.c = col_args(c);
+    apply_params(la.c, params);
+    la.c.wgs_update = 0;
+    la.c.w_in_slot = -1;
+    la.c.pf_dist = 0;
+    la.c.pdl = 0;
+    la.r = row_args(c);
+    la.r.pf_dist = 0;
+    la.r.pdl = 0;
+    la.r_last = la.r;
+    la.r_last.store_phase = 1;
+    la.n_iter = n_iter;
+    la.col_items = c->W / (nt / c->icol.tpl);
+    la.row_items = (c->h + lines - 1) / lines;
+    la.gbar = c->gbar;
+    la.epoch0 = c->gbar_epoch;
+    const int gx = la.col_items > la.row_items ? la.col_items : la.row_items;
+    const int e = launch_loop(c->H, c->pairs ? 2 : 1, gx, c->B, nt, c->stream, la, 0);
+    if (e) {
+        cudaGetLastError();
+        return SLMGS_ERR_CUDA;
+    }
+    c->gbar_epoch += (unsigned)(2 * n_iter - 1) * (unsigned)(gx * c->B);
+    c->launches++;
+    return SLMGS_OK;
+#endif
+}
+
 static int run_body(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
     int e;
     if (n_iter > 0) {
@@ -1365,6 +1449,11 @@ static int run_body(slmgs_ctx* c, const slmgs_params* params, int n_iter) {
         set_win(ra);
         ra.zero_acc2 = presum_slot(params);
         if ((e = run_row(c, ROW_FIRST, ra))) return e;
+        if (loop_eligible(c, params, n_iter)) {
+            if (run_loop(c, params, n_iter) == SLMGS_OK) return SLMGS_OK;
+            c->loop_bps = 0;  // the cooperative launch was refused: never again on this context, plain sequence from here
+            c->err.clear();
+        }
         for (int i = 0; i < n_iter; ++i) {
             const slmgs_params* p = params + i;
             ColArgs ca = col_args(c);

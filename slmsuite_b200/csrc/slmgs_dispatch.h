@@ -1,6 +1,7 @@
 // slmgs_dispatch.h -- per-size launchers (one translation unit per N, see slmgs_inst.cu).
 #pragma once
 #include "slmgs_teams.h"
+#include "slmgs_loop.h"
 
 namespace slmgs {
 
@@ -29,6 +30,7 @@ struct LaunchInfo {
     int launch_colp_##N_(int var, int dense, int gx, int gy, int nthreads, rt_stream s, const ColArgs& a);             \
     int launch_colt_##N_(int var, int dense, int gx, int gy, rt_stream s, const ColArgs& a, const void* tmap);         \
     int launch_rowt_##N_(int store, int dense, int gx, int gy, rt_stream s, const RowArgs& a);                        \
+    int launch_loop_##N_(int li, int gx, int gy, int nthreads, rt_stream s, const LoopArgs& a, int query_blocks_per_sm); \
     LaunchInfo launch_info_##N_();
 SLMGS_DECL(16)
 SLMGS_DECL(32)

@@ -178,6 +178,25 @@ int SLMGS_CAT(launch_colt_, SLMGS_N)(int, int, int, int, rt_stream, const ColArg
 int SLMGS_CAT(launch_rowt_, SLMGS_N)(int, int, int, int, rt_stream, const RowArgs&) { return -1; }
 #endif
 
+// the whole GS loop of a small square field in one cooperative kernel (slmgs_loop.h): 256 .. 1024 points per line.
+// query_blocks_per_sm != 0: return the resident blocks per SM at this geometry instead of launching.
+#if SLMGS_N >= 256 && SLMGS_N <= 1024 && !defined(SLMGS_EMULATE)
+template <int LI> static int launch_loop_li(int gx, int gy, int nthreads, rt_stream s, const LoopArgs& a, int query) {
+    typedef ColKernel<SLMGS_N, COL_FUSED, VAR_GS, 0, false> KC;
+    typedef RowKernel<SLMGS_N, ROW_FUSED, true, false, LI, false> KRS;
+    size_t smem = KC::smem_bytes(nthreads);
+    if (KRS::smem_bytes(nthreads) > smem) smem = KRS::smem_bytes(nthreads);
+    if (query) return loop_blocks_per_sm<SLMGS_N, LI>(nthreads, smem);
+    return launch_loop<SLMGS_N, LI>(gx, gy, nthreads, smem, s, a);
+}
+int SLMGS_CAT(launch_loop_, SLMGS_N)(int li, int gx, int gy, int nthreads, rt_stream s, const LoopArgs& a, int query) {
+    if (li == 2) return launch_loop_li<2>(gx, gy, nthreads, s, a, query);
+    return launch_loop_li<1>(gx, gy, nthreads, s, a, query);
+}
+#else
+int SLMGS_CAT(launch_loop_, SLMGS_N)(int, int, int, int, rt_stream, const LoopArgs&, int query) { return query ? 0 : -1; }
+#endif
+
 LaunchInfo SLMGS_CAT(launch_info_, SLMGS_N)() {
     typedef Fft<SLMGS_N> F;
     LaunchInfo i;

@@ -416,3 +416,26 @@ def test_team_kernels_batch_bit_identical(cuda, shape, batch, monkeypatch):
         del hb
     for a, b in zip(*out):
         assert a.tobytes() == b.tobytes()
+
+
+@pytest.mark.parametrize("n,slm", [(512, (512, 512)), (512, (300, 200)), (1024, (1024, 1024)), (256, (256, 256))])
+def test_loop_kernel_bit_identical(cuda, n, slm, monkeypatch):
+    """Small square fields run the whole GS loop in one cooperative kernel (csrc/slmgs_loop.h: the phases of the plain
+    kernels between grid barriers).  SLMGS_LOOP=1 and SLMGS_LOOP=0 agree bit for bit, and the loop kernel is really
+    used (far fewer launches)."""
+    from slmsuite_b200 import Hologram
+
+    rng = np.random.default_rng(31)
+    target = rng.random((n, n), dtype=np.float32)
+    phase = rng.uniform(-np.pi, np.pi, slm).astype(np.float32)
+    out = []
+    for loop in ("1", "0"):
+        monkeypatch.setenv("SLMGS_LOOP", loop)
+        monkeypatch.setenv("SLMGS_SPARSE", "0")
+        h = Hologram(target, phase=phase, slm_shape=slm)
+        h.optimize("GS", maxiter=12, verbose=False)
+        out.append((h.phase.copy(), h.amp_ff.copy(), h._lib.slmgs_launch_count(h._ctx)))
+        del h
+    assert out[0][0].tobytes() == out[1][0].tobytes()
+    assert out[0][1].tobytes() == out[1][1].tobytes()
+    assert out[0][2] < out[1][2] - 10

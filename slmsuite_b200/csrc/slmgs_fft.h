@@ -289,11 +289,11 @@ template <int N> struct Fft {
         }
     }
 
-    // ---- stages with L1-burst hooks (ping-pong teams, slmgs_launch.h: slmgs_kernel_pp) -------------------
+    // ---- stages split at their shared-memory bursts (team kernels, slmgs_teams.h) -------------------
     // Same arithmetic as fwd_stage / inv_stage, ordered as  [shared-memory reads] release | butterflies + twiddles |
-    // acquire [shared-memory writes]:  `sy` brackets the bursts on the L1 / shared-memory data pipe so that two teams
-    // of one block alternate on it (one team's exchange runs under the other's butterflies).  Stage S == 0 of the
-    // forward (S == NS-1 of the inverse) has no read burst: the caller releases after its global loads.
+    // acquire [shared-memory writes].  `sy` are hooks around the bursts on the L1 / shared-memory data pipe: no-ops
+    // (NoSync) in the product kernels; the token / mutex experiments of DESIGN.md 4.10 (tools/micro/pp_token.h) plugged
+    // their hand-offs in here.  Stage S == 0 of the forward (S == NS-1 of the inverse) has no read burst.
     template <int S, int U, class TP> static SLMGS_DEVICE void fwd_twiddle_u(cf* v, int lt, TP twA, TP twB) {
         constexpr int R = radix<S>();
         if constexpr (U < E / R) {

@@ -460,35 +460,6 @@ template <int N, int MODE, bool STORE = false, bool SPARSE = false, int LI = 1, 
         }
     }
 
-    // ROW_FUSED with L1-burst hooks (two ping-pong teams per block, slmgs_kernel_pp); see ColKernel::phase_sy
-    static constexpr int PP_THREADS = TEAM;
-    static SLMGS_DEVICE int pp_items(const Args& a) { return (a.h + LI - 1) / LI; }
-    template <int P, class Sy>
-    static SLMGS_DEVICE void phase_sy(State& st, const Args& a, cf* smem, const ThreadId& id, Sy& sy) {
-        static_assert(MODE == ROW_FUSED, "ping-pong teams: fused row kernel");
-        const Loc L = locate(a, smem, id);
-        if constexpr (P == 0) {
-            if (a.zero_acc && id.bx == 0 && id.tid == 0) a.zero_acc[(long long)id.by * a.zero_bs] = 0.0;
-            if (a.zero_acc2 && id.bx == 0 && id.tid == 0) a.zero_acc2[(long long)id.by * a.zero_bs] = 0.0;
-            if (a.win_dst && id.bx == 0 && id.tid == 0)
-                a.win_dst[id.by] = (float)(1.0 / sqrt(a.win_src[(long long)id.by * a.zero_bs]));
-            load_spectrum(st, a, L);
-            sy.release();
-        }
-        if constexpr (P < NS - 1) {
-            F::template inv_stage_sy<NS - 1 - P>(st.v, L.lt, a.twA, a.twB, L.s, LI, sy);
-        } else if constexpr (P == NS - 1) {
-            F::template inv_stage_sy<0>(st.v, L.lt, a.twA, a.twB, L.s, LI, sy);
-            project<true, STORE>(st, a, id, L);
-            F::template fwd_stage_sy<0>(st.v, L.lt, a.twA, a.twB, L.s, LI, sy);
-        } else {
-            F::template fwd_stage_sy<P - (NS - 1)>(st.v, L.lt, a.twA, a.twB, L.s, LI, sy);
-        }
-        if constexpr (P == NPHASE - 1) {
-            sy.acquire();
-            store_spectrum(st, a, L);
-        }
-    }
 };
 
 // ==========================================================================================
@@ -934,34 +905,6 @@ template <int N, int MODE, int VAR = 0, int CT = 0, bool DENSE = false> struct C
         }
     }
 
-    // The fused phases with L1-burst hooks (two ping-pong teams per block, slmgs_kernel_pp): one release and one
-    // acquire per phase; the token is held across the team barrier between phases (shared-memory writes of phase P,
-    // reads of phase P + 1) and from a tile's global stores to the next tile's global loads.
-    static constexpr int PP_THREADS = CT > 0 ? CT * F::TPL : 0;  // threads of a team
-    static SLMGS_DEVICE int pp_items(const Args& a) { return a.W / (CT > 0 ? CT : 1); }
-    template <int P, class Sy>
-    static SLMGS_DEVICE void phase_sy(State& st, const Args& a, cf* smem, const ThreadId& id, Sy& sy) {
-        static_assert(MODE == COL_FUSED && CT > 0, "ping-pong teams: fused column kernel with a compile-time tile width");
-        const Loc L = locate(a, smem, id);
-        if constexpr (P == 0) {
-            load_rows(st, a, L);
-            sy.release();
-            F::template fwd_stage_sy<0>(st.v, L.lt, a.twA, a.twB, L.s, L.C, sy);
-        } else if constexpr (P < NS - 1) {
-            F::template fwd_stage_sy<P>(st.v, L.lt, a.twA, a.twB, L.s, L.C, sy);
-        } else if constexpr (P == NS - 1) {
-            prefetch_images_head(a, L);
-            F::template fwd_stage_sy<NS - 1>(st.v, L.lt, a.twA, a.twB, L.s, L.C, sy);
-            constrain<false>(st, a, id, L);
-            F::template inv_stage_sy<NS - 1>(st.v, L.lt, a.twA, a.twB, L.s, L.C, sy);
-        } else {
-            F::template inv_stage_sy<2 * NS - 2 - P>(st.v, L.lt, a.twA, a.twB, L.s, L.C, sy);
-            if constexpr (P == NPHASE - 1) {
-                sy.acquire();
-                store_rows(st, a, L);
-            }
-        }
-    }
 };
 
 // ==========================================================================================

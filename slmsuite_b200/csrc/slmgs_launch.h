@@ -21,11 +21,6 @@
 
 namespace slmgs {
 
-struct NoSyncEmu {
-    void acquire() {}
-    void release() {}
-};
-
 struct ThreadId {
     int tid;       // threadIdx.x
     int nthreads;  // blockDim.x
@@ -180,17 +175,7 @@ int launch_kernel(int gx, int gy, int nthreads, size_t smem_bytes, cudaStream_t 
     return (int)cudaGetLastError();
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// Ping-pong teams.  slmgs_kernel_pp<K> runs TWO independent teams of K::PP_THREADS threads in one persistent block
-// (one block per SM); each team walks over its own work items (column tiles / row groups) with its own shared-memory
-// slice and its own named barrier.  Two equal blocks that start together on one SM stay in lock step: both queue
-// their shared-memory exchange at the same time, both wait for it, then both compete for the FMA pipe -- the L1 /
-// shared-memory data pipe and the FMA pipe take turns instead of overlapping (ncu: each ~50 % busy).  Here the bursts on the L1 data
-// pipe (global loads / stores, exchange writes + reads) are bracketed by a token that the teams hand back and forth
-// (bar.sync / bar.arrive on two named barriers, K::phase_sy): team B's burst always queues behind team A's, so A's
-// butterflies run under B's exchange and vice versa.
-// Every phase releases and acquires exactly once; a team holds the token at phase boundaries.
-// ------------------------------------------------------------------------------------------------------------------
+// development trace of the team kernels (tools/micro/pp_bench.cu, -DSLMGS_PP_TRACE): clock stamps of one thread per team
 #ifdef SLMGS_PP_TRACE
 #ifndef SLMGS_PP_TRACE_TID
 #define SLMGS_PP_TRACE_TID 0
@@ -216,90 +201,6 @@ SLMGS_DEVICE void pp_stamp(int team, int kind) {
 #else
 #define SLMGS_PP_STAMP(team, kind)
 #endif
-template <int T> struct TeamSync {
-    int mine, other;  // named barriers: `mine` = this team waits here for the token, `other` = the partner does
-    SLMGS_DEVICE void acquire() {
-        SLMGS_PP_STAMP(mine - 3, 0);
-        asm volatile("bar.sync %0, %1;" ::"r"(mine), "n"(2 * T) : "memory");
-        SLMGS_PP_STAMP(mine - 3, 1);
-    }
-    SLMGS_DEVICE void release() {
-        asm volatile("bar.arrive %0, %1;" ::"r"(other), "n"(2 * T) : "memory");
-        SLMGS_PP_STAMP(mine - 3, 2);
-    }
-};
-template <class K, int P, class Sy>
-SLMGS_DEVICE void run_phases_pp(typename K::State& st, const typename K::Args& a, cf* smem, const ThreadId& id, Sy& sy,
-                                int team, bool active) {
-    if (active) {
-        K::template phase_sy<P>(st, a, smem, id, sy);
-    } else {  // a team without a work item in the last round keeps the token moving
-        sy.release();
-        sy.acquire();
-    }
-    if constexpr (P + 1 < K::NPHASE) {
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(K::PP_THREADS) : "memory");
-        SLMGS_PP_STAMP(team, 3);
-        run_phases_pp<K, P + 1>(st, a, smem, id, sy, team, active);
-    }
-}
-template <class K> __global__ void __launch_bounds__(2 * K::PP_THREADS, 1) slmgs_kernel_pp(const typename K::Args a, int team_smem_cf) {
-    extern __shared__ __align__(16) unsigned char slmgs_smem_raw[];
-    constexpr int T = K::PP_THREADS;
-    const int team = threadIdx.x / T;
-    SLMGS_PP_STAMP(team, 6);
-    cf* smem = reinterpret_cast<cf*>(slmgs_smem_raw) + (size_t)team * team_smem_cf;
-    typename K::State st;
-    ThreadId id;
-    id.tid = threadIdx.x % T;
-    id.nthreads = T;
-    id.by = blockIdx.y;
-    id.it = 0;
-    asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int items = K::pp_items(a);
-    id.gx = items;
-    const int stride = 2 * gridDim.x;
-    const int rounds = (items + stride - 1) / stride;
-    TeamSync<T> sy;
-    sy.mine = 3 + team;
-    sy.other = 4 - team;
-    if (team == 1) sy.release();  // team 0 starts with the token
-    sy.acquire();
-    for (int r = 0; r < rounds; ++r) {
-        id.bx = 2 * blockIdx.x + team + r * stride;
-        run_phases_pp<K, 0>(st, a, smem, id, sy, team, id.bx < items);
-        // the exchange buffer is written again in phase 0 of the next item
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(T) : "memory");
-    }
-    if (team == 0) sy.release();
-}
-
-// gx: persistent blocks per hologram (<= number of SMs); team_threads = K::PP_THREADS (host copy of the constant)
-template <class K>
-int launch_kernel_pp(int gx, int gy, size_t team_smem_bytes, cudaStream_t stream, const typename K::Args& a, bool pdl = false) {
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!attr_set[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(slmgs_kernel_pp<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-        if (e != cudaSuccess) return (int)e;
-        attr_set[dev & 63] = true;
-    }
-    const size_t team_cf = (team_smem_bytes + sizeof(cf) - 1) / sizeof(cf);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3(gx, gy, 1);
-    cfg.blockDim = dim3(2 * K::PP_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = 2 * team_cf * sizeof(cf);
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    return (int)cudaLaunchKernelEx(&cfg, slmgs_kernel_pp<K>, a, (int)team_cf);
-}
 #else
 template <class K, int P>
 inline void emu_phases(std::vector<typename K::State>& st, const typename K::Args& a, cf* smem, ThreadId id) {
@@ -340,35 +241,6 @@ int launch_kernel(int gx, int gy, int nthreads, size_t smem_bytes, void* /*strea
     return 0;
 }
 
-// ping-pong kernels under emulation: the hooked phases (phase_sy) of every work item, one after the other
-template <class K, int P>
-inline void emu_phases_pp(std::vector<typename K::State>& st, const typename K::Args& a, cf* smem, ThreadId id) {
-    NoSyncEmu sy;
-    for (int t = 0; t < id.nthreads; ++t) {
-        id.tid = t;
-        K::template phase_sy<P>(st[t], a, smem, id, sy);
-    }
-    if constexpr (P + 1 < K::NPHASE) emu_phases_pp<K, P + 1>(st, a, smem, id);
-}
-template <class K>
-int launch_kernel_pp(int /*gx*/, int gy, size_t team_smem_bytes, void* /*stream*/, const typename K::Args& a, bool /*pdl*/ = false) {
-    const int T = K::PP_THREADS;
-    std::vector<typename K::State> st(T);
-    std::vector<cf> smem(team_smem_bytes / sizeof(cf) + 2);
-    const int items = K::pp_items(a);
-    for (int by = 0; by < gy; ++by)
-        for (int bx = 0; bx < items; ++bx) {
-            ThreadId id;
-            id.tid = 0;
-            id.nthreads = T;
-            id.bx = bx;
-            id.by = by;
-            id.gx = items;
-            id.it = 0;
-            emu_phases_pp<K, 0>(st, a, smem.data(), id);
-        }
-    return 0;
-}
 #endif
 
 }  // namespace slmgs

@@ -6,6 +6,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -DSLMGS_PACKED_F32X2
 //             -DSLMGS_TW_PRODUCTS -I slmsuite_b200/csrc -o tools/micro/pp_bench tools/micro/pp_bench.cu
 #include "slmgs_teams.h"
+#include "pp_token.h"
 
 #include <cuda.h>
 
@@ -46,6 +47,8 @@ typedef ColKernel<NN, COL_FUSED, VAR_GS, 2, true> KCol;
 typedef RowKernel<NN, ROW_FUSED, false, false, 2, true> KRow;
 typedef ColKernelT<NN, VAR_GS, true> KColT;
 typedef RowKernelT<NN, false, true> KRowT;
+typedef PPCol<KCol> KColPP;
+typedef PPRow<KRow, 2> KRowPP;
 typedef ColKernel<NN, COL_FUSED, VAR_POW, 2, true> KColPow;
 typedef ColKernelT<NN, VAR_POW, true> KColPowT;
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -152,13 +155,13 @@ int main(int argc, char** argv) {
     ca.fld = fld1;
     CK(launch_kernel<KCol>(W / 2, 1, 512, col_smem, 0, ca));
     ca.fld = fld2;
-    CK(launch_kernel_pp<KCol>(pgx, 1, col_smem, 0, ca));
+    CK(launch_kernel_pp<KColPP>(pgx, 1, col_smem, 0, ca));
     CK(cudaDeviceSynchronize());
     check("column kernel");
     ra.fld = fld1;
     CK(launch_kernel<KRow>(H / 2, 1, 512, row_smem, 0, ra));
     ra.fld = fld2;
-    CK(launch_kernel_pp<KRow>(pgx, 1, row_smem, 0, ra));
+    CK(launch_kernel_pp<KRowPP>(pgx, 1, row_smem, 0, ra));
     CK(cudaDeviceSynchronize());
     check("row kernel");
     CUtensorMap tmap1 = make_tmap(fld1, H, W);
@@ -184,8 +187,8 @@ int main(int argc, char** argv) {
             CK(cudaMemcpyToSymbol(slmgs_pp_trace_n, zero, sizeof zero));
             if (which == 3) { ra.fld = fld2; CK(launch_kernel_teams<KRowT>(pgx, 1, 0, ra)); }
             else if (which == 2) { ca.fld = fld2; CK(launch_kernel_teams<KColT>(pgx, 1, 0, ca, tmap2)); }
-            else if (which == 0) { ca.fld = fld2; CK(launch_kernel_pp<KCol>(pgx, 1, col_smem, 0, ca)); }
-            else { ra.fld = fld2; CK(launch_kernel_pp<KRow>(pgx, 1, row_smem, 0, ra)); }
+            else if (which == 0) { ca.fld = fld2; CK(launch_kernel_pp<KColPP>(pgx, 1, col_smem, 0, ca)); }
+            else { ra.fld = fld2; CK(launch_kernel_pp<KRowPP>(pgx, 1, row_smem, 0, ra)); }
             CK(cudaDeviceSynchronize());
             static long long buf[2 * 512];
             int n[2];
@@ -213,7 +216,7 @@ int main(int argc, char** argv) {
     float t;
     t = time_ms(reps, [&]() { CK(launch_kernel<KCol>(W / 2, 1, 512, col_smem, 0, ca)); });
     printf("col plain     : %8.2f us  %7.1f GB/s\n", t * 1e3, colB / t * 1e-6);
-    t = time_ms(reps, [&]() { CK(launch_kernel_pp<KCol>(pgx, 1, col_smem, 0, ca)); });
+    t = time_ms(reps, [&]() { CK(launch_kernel_pp<KColPP>(pgx, 1, col_smem, 0, ca)); });
     printf("col ping-pong : %8.2f us  %7.1f GB/s\n", t * 1e3, colB / t * 1e-6);
     t = time_ms(reps, [&]() { CK(launch_kernel_teams<KColT>(pgx, 1, 0, ca, tmap1)); });
     printf("col TMA teams : %8.2f us  %7.1f GB/s\n", t * 1e3, colB / t * 1e-6);
@@ -221,12 +224,8 @@ int main(int argc, char** argv) {
     printf("row plain     : %8.2f us  %7.1f GB/s\n", t * 1e3, rowB / t * 1e-6);
     t = time_ms(reps, [&]() { CK(launch_kernel_teams<KRowT>(pgx, 1, 0, ra)); });
     printf("row TMA teams : %8.2f us  %7.1f GB/s\n", t * 1e3, rowB / t * 1e-6);
-    t = time_ms(reps, [&]() { CK(launch_kernel_pp<KRow>(pgx, 1, row_smem, 0, ra)); });
+    t = time_ms(reps, [&]() { CK(launch_kernel_pp<KRowPP>(pgx, 1, row_smem, 0, ra)); });
     printf("row ping-pong : %8.2f us  %7.1f GB/s\n", t * 1e3, rowB / t * 1e-6);
-    t = time_ms(reps, [&]() {
-        CK(launch_kernel<KCol>(W / 2, 1, 512, col_smem, 0, ca, true));
-        CK(launch_kernel<KRow>(H / 2, 1, 512, row_smem, 0, ra, true));
-    });
     {   // WGS (power-law update): weights read + written, target read -- timing only (the weights evolve)
         float* target;
         CK(cudaMalloc(&target, P * sizeof(float)));
@@ -240,10 +239,14 @@ int main(int argc, char** argv) {
         t = time_ms(reps, [&]() { CK(launch_kernel_teams<KColPowT>(pgx, 1, 0, cw, tmap1)); });
         printf("col WGS TMA teams : %8.2f us  %7.1f GB/s\n", t * 1e3, powB / t * 1e-6);
     }
+    t = time_ms(reps, [&]() {
+        CK(launch_kernel<KCol>(W / 2, 1, 512, col_smem, 0, ca, true));
+        CK(launch_kernel<KRow>(H / 2, 1, 512, row_smem, 0, ra, true));
+    });
     printf("iteration plain (PDL)     : %8.2f us -> %6.0f it/s\n", t * 1e3, 1e3 / t);
     t = time_ms(reps, [&]() {
-        CK(launch_kernel_pp<KCol>(pgx, 1, col_smem, 0, ca, true));
-        CK(launch_kernel_pp<KRow>(pgx, 1, row_smem, 0, ra, true));
+        CK(launch_kernel_pp<KColPP>(pgx, 1, col_smem, 0, ca, true));
+        CK(launch_kernel_pp<KRowPP>(pgx, 1, row_smem, 0, ra, true));
     });
     printf("iteration ping-pong (PDL) : %8.2f us -> %6.0f it/s\n", t * 1e3, 1e3 / t);
     t = time_ms(reps, [&]() {

@@ -33,6 +33,36 @@ __device__ __forceinline__ float2 math_loop(int iters, float2 seed) {
     for (int i = 0; i < 8; ++i) { s.x += a[i].x; s.y += a[i].y; }
     return s;
 }
+// radix-2 butterflies: (a, b) -> (a + b, a - b): both FADD2 of a pair read the same two register pairs (operand reuse cache)
+__device__ __forceinline__ float2 bfly_loop(int iters, float2 seed) {
+    float2 a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = make_float2(seed.x + i, seed.y - i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = i + 4;
+                const float2 x = __fadd2_rn(a[i], a[j]);
+                const float2 y = __fadd2_rn(a[i], make_float2(-a[j].x, -a[j].y));
+                a[i] = x;
+                a[j] = make_float2(y.x * 0.5f, y.y * 0.5f) ;
+                a[i] = make_float2(a[i].x * 0.5f, a[i].y * 0.5f);
+            }
+        }
+    }
+    float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s.x += a[i].x; s.y += a[i].y; }
+    return s;
+}
+__global__ void __launch_bounds__(1024, 1) kb(int mi, float2* out) {
+    const int w = threadIdx.x >> 5;
+    float2 r = make_float2(0.f, 0.f);
+    if (w < 16) r = bfly_loop(mi, make_float2((float)threadIdx.x, 1.0f));
+    if (r.x == 123.456f) out[threadIdx.x] = r;
+}
 
 // 16 x (LDS.64 + STS.64) per iteration, conflict free (consecutive lanes, consecutive 8-byte words)
 __device__ __forceinline__ float2 smem_loop(int iters, float2* s, int lane_base) {
@@ -103,6 +133,22 @@ int main() {
         const double f = 1965.0 / (4.0 * mi * 32);
         printf("distinct operands, clk per warp-instr per SMSP: FADD2 %.2f  FFMA2(3 regs) %.2f  FMUL2 %.2f  FFMA2(swizzled cmul form) %.2f\n", t2 * f, t3 * f, t4 * f, t5 * f);
         printf("with the shared-memory warps running too: FADD2 %.1f us (alone %.1f), FFMA2 %.1f us (alone %.1f)\n", b2, t2, b3, t3);
+    }
+    {
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        kb<<<148, 1024>>>(mi, out);
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0));
+        kb<<<148, 1024>>>(mi, out);
+        CK(cudaEventRecord(e1));
+        CK(cudaDeviceSynchronize());
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        // per iteration and warp: 16 butterflies = 32 FADD2 + 32 FMUL2 (scaling by 0.5 keeps the values finite)
+        printf("butterfly pairs (a+b, a-b) + 2 FMUL2 by an immediate each: %.2f clk per packed instruction per SMSP\n",
+               ms * 1e3 * 1965.0 / (4.0 * mi * 64));
     }
     {
         const float tm = run<1>(1, mi, si, out), ts = run<1>(2, mi, si, out), tb = run<1>(3, mi, si, out);

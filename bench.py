@@ -613,14 +613,15 @@ def run_b200(args, rank, local_rank, world):
         "kernel_share_of_step": {k: v / tot for k, v in share.items()},
         # second roofline of the same kernels: the FP32 pipe.  Packed FADD2 / FMUL2 take 2 clk per warp and
         # SMSP, FFMA2 with three register operands 3 clk (tools/micro/pipe_overlap.cu); per thread (16 points) the fused column
-        # kernel issues 384 + 162 + 152 of them plus ~250 scalar FMA-pipe instructions = ~1800 clk, the row kernel ~1750
+        # kernel issues 384 FADD2 (2.07 clk) + 104 complex multiplies (FMUL2 + FFMA2: 4.43 clk per pair) + 58 + 48 constant
+        # twiddle FMUL2 / FFMA2 (2.07 / 2.26) + ~150 scalar FMA-pipe instructions = ~1650 clk, the row kernel ~1600
         "fp32_pipe": (lambda clk: {
             "what": "FP32-pipe time of the launch (SASS instruction counts x measured issue cost, all SMs busy) / measured time",
             "lane_clk_per_thread": clk,
             "floor_ms": {k: (P / 16 / 32) * clk[k] / (148 * 4) / (clocks.get("sm_mhz", 1965.0) * 1e3) for k in clk},
             "frac": {k: (P / 16 / 32) * clk[k] / (148 * 4) / (clocks.get("sm_mhz", 1965.0) * 1e3) / kern[k]["avg_ms"]
                      for k in clk if k in kern},
-        })({"col_fused": 1800.0, "row_fused": 1750.0}),
+        })({"col_fused": 1650.0, "row_fused": 1600.0}),
         "measured": "CUDA events around every launch of the same K steps, repeated right after the timed region",
         "kernels": kern,
     }

@@ -23,6 +23,13 @@ __device__ __forceinline__ float2 math_loop(int iters, float2 seed) {
                 else if (MATHMODE == 2) a[i] = __fadd2_rn(a[i], a[(i + 3) & 7]);
                 else if (MATHMODE == 3) a[i] = __ffma2_rn(a[i], a[(i + 1) & 7], a[(i + 3) & 7]);
                 else if (MATHMODE == 4) a[i] = __fmul2_rn(a[i], a[(i + 3) & 7]);
+                else if (MATHMODE == 6) {  // full complex multiply, the library's form: FMUL2 + FFMA2 sharing the operand a
+                    const float2 x = a[i], w = a[(i + 3) & 7];
+                    a[i] = __ffma2_rn(make_float2(-x.y, x.x), make_float2(w.y, w.y), __fmul2_rn(x, make_float2(w.x, w.x)));
+                } else if (MATHMODE == 7) {  // the same with scalar instructions
+                    const float2 x = a[i], w = a[(i + 3) & 7];
+                    a[i] = make_float2(fmaf(-x.y, w.y, x.x * w.x), fmaf(x.y, w.x, x.x * w.y));
+                }
                 else if (MATHMODE == 5) a[i] = __ffma2_rn(make_float2(-a[(i + 1) & 7].y, a[(i + 1) & 7].x), make_float2(a[(i + 2) & 7].y, a[(i + 2) & 7].y), a[i]);
                 else { a[i].x = fmaf(a[i].x, m.x, c.x); a[i].y = fmaf(a[i].y, m.y, c.y); }
             }
@@ -120,6 +127,8 @@ int main() {
     CK(cudaFuncSetAttribute(k<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 512 * 8));
     CK(cudaFuncSetAttribute(k<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 512 * 8));
     CK(cudaFuncSetAttribute(k<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 512 * 8));
+    CK(cudaFuncSetAttribute(k<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 512 * 8));
+    CK(cudaFuncSetAttribute(k<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 512 * 8));
     const int mi = 2000, si = 1000;
     // math: 16 warps x mi x 32 instructions; smem: 16 warps x si x 32 instructions (2 wavefronts each)
     {
@@ -132,6 +141,10 @@ int main() {
         const float b2 = run<2>(3, mi, si, out), b3 = run<3>(3, mi, si, out);
         const double f = 1965.0 / (4.0 * mi * 32);
         printf("distinct operands, clk per warp-instr per SMSP: FADD2 %.2f  FFMA2(3 regs) %.2f  FMUL2 %.2f  FFMA2(swizzled cmul form) %.2f\n", t2 * f, t3 * f, t4 * f, t5 * f);
+        {
+            const float t6 = run<6>(1, mi, si, out), t7 = run<7>(1, mi, si, out);
+            printf("complex multiply: packed (FMUL2 + FFMA2) %.2f clk per multiply, scalar (2 FMUL + 2 FFMA) %.2f clk per multiply\n", t6 * f, t7 * f);
+        }
         printf("with the shared-memory warps running too: FADD2 %.1f us (alone %.1f), FFMA2 %.1f us (alone %.1f)\n", b2, t2, b3, t3);
     }
     {

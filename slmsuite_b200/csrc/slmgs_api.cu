@@ -146,6 +146,7 @@ struct slmgs_ctx {
     float* stage_f;   // staging for rolled uploads/downloads (B*H*W floats)
     float *phase, *amp, *prop, *target, *weights, *phase_ff, *amp_ff;
     cf *twA_row, *twB_row, *twA_col, *twB_col;
+    cf *twA_half, *twB_half;  // tables of H / 2 points (ColKernelT8), or nullptr
     double* acc;      // [B][ACC_N]
     float* winf;      // [B] 1/sqrt(sum w^2) of the pending normalisation, written by the row kernels of the fused loop
     double* partial;  // stats partials
@@ -220,6 +221,8 @@ struct slmgs_ctx {
     // persistent fused column kernel with TMA-staged tiles (ColKernelP)
     // team kernels (slmgs_teams.h): TMA-staged tiles, two compute teams per persistent block
     bool teams_col, teams_row;  // used for the COL_FUSED / ROW_FUSED launches of the dense-far-field loop
+    bool teams_col8;            // dense 8192-point columns: COL_FUSED / COL_FWD as ColKernelT8 (two interleaved 4096-point lines)
+    unsigned char tmap_col1[128] __attribute__((aligned(64)));  // ... its CUtensorMap: box {1 column x 2 row parities, 256 row pairs}
     int tb_pairs, tb_n, tb_lo, tb_hi0;  // TMA boxes of a column tile (ColArgs)
     unsigned char tmap_pairs[128] __attribute__((aligned(64)));  // host copy of the CUtensorMap over the row-pair interleaved fld
     bool colp;                 // used for COL_FUSED launches of this context
@@ -474,6 +477,35 @@ static bool setup_teams_col(slmgs_ctx* c) {
     return true;
 }
 
+// ColKernelT8 (dense 8192-point columns as two interleaved 4096-point lines): twiddle tables of the half length and a
+// tensor map over the row-pair interleaved fld with box {1 column x 2 row parities (16 bytes), 256 row pairs, 1}
+static bool setup_teams_col8(slmgs_ctx* c) {
+#ifndef SLMGS_EMULATE
+    std::vector<cf> a, b;
+    make_twiddles(c->H / 2, a, b);
+    if (dev_alloc(c, &c->twA_half, a.size()) || dev_alloc(c, &c->twB_half, b.size())) return false;
+    if (rt_h2d(c->twA_half, a.data(), a.size() * sizeof(cf), c->stream) || rt_h2d(c->twB_half, b.data(), b.size() * sizeof(cf), c->stream))
+        return false;
+    if (rt_sync(c->stream)) return false;  // (a, b are about to go out of scope)
+    slmgs_encode_fn encode = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&encode, cudaEnableDefault, &qres) != cudaSuccess || !encode) {
+        cudaGetLastError();
+        return false;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)c->W * 2, (cuuint64_t)c->H / 2, (cuuint64_t)c->B};
+    cuuint64_t strides[2] = {(cuuint64_t)c->W * 2 * sizeof(cf), (cuuint64_t)c->W * c->H * sizeof(cf)};
+    cuuint32_t box[3] = {2, 256, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return encode(reinterpret_cast<CUtensorMap*>(c->tmap_col1), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, c->fld, dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+#else
+    (void)c;
+    return false;
+#endif
+}
+
 extern "C" int slmgs_version(void) { return 100; }
 
 
@@ -501,6 +533,7 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
     c->fld = nullptr; c->farfield = nullptr; c->stage_c = nullptr; c->stage_f = nullptr;
     c->phase = c->amp = c->prop = c->target = c->weights = c->phase_ff = c->amp_ff = nullptr;
     c->twA_row = c->twB_row = c->twA_col = c->twB_col = nullptr;
+    c->twA_half = c->twB_half = nullptr;
     c->acc = nullptr; c->partial = nullptr; c->winf = nullptr;
     c->spot_x = c->spot_y = nullptr; c->spot_amp = nullptr; c->spot_pw = nullptr; c->n_spots = 0;
     c->spot_wn = nullptr; c->spot_keep = nullptr;
@@ -536,6 +569,7 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
     c->graph_clock = 0;
 #endif
     c->teams_col = c->teams_row = false;
+    c->teams_col8 = false;
     c->weights_pristine = false;
     c->gbar = nullptr;
     c->gbar_epoch = 0;
@@ -608,6 +642,9 @@ extern "C" int slmgs_create(slmgs_ctx** out, int device, int batch, int H, int W
         const long long teams_gpu = 2LL * c->sms;
         if ((long long)(c->h / 2) * c->B < 4 * teams_gpu) c->teams_row = false;
         if ((long long)(c->W / 2) * c->B < 4 * teams_gpu) c->teams_col = false;
+        // (opt-in: measured SLOWER than the plain 8192 kernels on B200 -- 16-byte TMA rows and half-used sectors)
+        c->teams_col8 = on && env_int("SLMGS_TEAMS8", 0) != 0 && c->H == 8192 && c->h == c->H && c->col_threads == 2 * c->icol.tpl &&
+                        (long long)c->W * c->B >= 4 * teams_gpu && setup_teams_col8(c);
     }
     CR(rt_check(c, rt_sync(c->stream), "sync"));
 #undef CR
@@ -620,7 +657,7 @@ extern "C" int slmgs_destroy(slmgs_ctx* c) {
     rt_set_device(c->device);
     if (c->stream) rt_sync(c->stream);
     void* ptrs[] = {c->fld, c->farfield, c->stage_c, c->stage_f, c->phase, c->amp, c->prop, c->target,
-                    c->weights, c->phase_ff, c->amp_ff, c->twA_row, c->twB_row, c->twA_col, c->twB_col, c->acc,
+                    c->weights, c->phase_ff, c->amp_ff, c->twA_row, c->twB_row, c->twA_col, c->twB_col, c->twA_half, c->twB_half, c->acc,
                     c->partial, c->spot_x, c->spot_y, c->spot_amp, c->spot_pw, c->spot_wn, c->spot_keep, c->phase_saved, c->mp_sum, c->zero_w,
                     c->tile_flags, c->tile_list, c->tile_byte, c->tile_count, c->samp_y, c->samp_x, c->scratch, c->winf,
                     c->tmap_dev, c->gbar};
@@ -928,6 +965,8 @@ static ColArgs col_args(slmgs_ctx* c) {
     a.fld_bs = (long long)c->H * c->W;
     a.twA = c->twA_col;
     a.twB = c->twB_col;
+    a.tw2A = c->twA_half;
+    a.tw2B = c->twB_half;
     a.weights = c->weights;
     a.target = c->target;
     a.phase_ff = c->phase_ff;
@@ -1040,6 +1079,10 @@ static int run_col(slmgs_ctx* c, int mode, const ColArgs& a) {
         const int pgx = teams_blocks(c, c->icol, c->W / 2);
         e = rt_check(c, launch_colt(c->H, var, c->h == c->H ? 1 : 0, pgx, c->B, c->stream, a, c->tmap_pairs),
                      "team column kernel launch");
+    } else if ((mode == COL_FUSED || mode == COL_FWD) && c->teams_col8 && !a.tiles && !a.store_farfield && !a.store_phaseff) {
+        int pgx = c->sms / c->B;
+        if (pgx < 1) pgx = 1;
+        e = rt_check(c, launch_colt8(mode, var, pgx, c->B, c->stream, a, c->tmap_col1), "team column kernel launch (8192)");
     } else if (mode == COL_FUSED && c->colp) {
         // persistent: about one block per SM over the whole batch, each walking over its share of the tiles
         int pgx = c->sms / c->B;
@@ -1709,7 +1752,7 @@ static int update_weights_spot_impl(slmgs_ctx* c, const slmgs_params* p, int wid
     if (e) return e;
     c->launches++;
     c->weights_pristine = false;
-    return rt_check(c, launch_kernel<SpotUpdateKernel>(1, c->B, 1024, (1024 + 8) * sizeof(double), c->stream, a), "spot update launch");
+    return rt_check(c, launch_kernel<SpotUpdateKernel>(1, c->B, 1024, (1024 + 8 + 32) * sizeof(double), c->stream, a), "spot update launch");
 }
 
 extern "C" int slmgs_update_weights_spot(slmgs_ctx* c, const slmgs_params* p, int width) {

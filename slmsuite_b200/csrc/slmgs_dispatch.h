@@ -32,6 +32,8 @@ struct LaunchInfo {
     int launch_rowt_##N_(int store, int dense, int gx, int gy, rt_stream s, const RowArgs& a);                        \
     int launch_loop_##N_(int li, int gx, int gy, int nthreads, rt_stream s, const LoopArgs& a, int query_blocks_per_sm); \
     LaunchInfo launch_info_##N_();
+// 8192-point columns on the team design (ColKernelT8, slmgs_teams.h): mode COL_FUSED / COL_FWD; -1 = not available
+int launch_colt8(int mode, int var, int gx, int gy, rt_stream s, const ColArgs& a, const void* tmap);
 SLMGS_DECL(16)
 SLMGS_DECL(32)
 SLMGS_DECL(64)

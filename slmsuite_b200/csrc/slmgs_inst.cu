@@ -178,6 +178,24 @@ int SLMGS_CAT(launch_colt_, SLMGS_N)(int, int, int, int, rt_stream, const ColArg
 int SLMGS_CAT(launch_rowt_, SLMGS_N)(int, int, int, int, rt_stream, const RowArgs&) { return -1; }
 #endif
 
+#if SLMGS_N == 8192
+#ifndef SLMGS_EMULATE
+int launch_colt8(int mode, int var, int gx, int gy, rt_stream s, const ColArgs& a, const void* tmap) {
+    const CUtensorMap& tm = *reinterpret_cast<const CUtensorMap*>(tmap);
+    if (mode == COL_FWD) return launch_kernel_teams<ColKernelT8<COL_FWD, VAR_GENERAL> >(gx, gy, s, a, tm, a.pdl != 0);
+    if (mode != COL_FUSED) return -1;
+    switch (var) {
+        case VAR_GS: return launch_kernel_teams<ColKernelT8<COL_FUSED, VAR_GS> >(gx, gy, s, a, tm, a.pdl != 0);
+        case VAR_POW: return launch_kernel_teams<ColKernelT8<COL_FUSED, VAR_POW> >(gx, gy, s, a, tm, a.pdl != 0);
+        case VAR_POW_STORED: return launch_kernel_teams<ColKernelT8<COL_FUSED, VAR_POW_STORED> >(gx, gy, s, a, tm, a.pdl != 0);
+        default: return launch_kernel_teams<ColKernelT8<COL_FUSED, VAR_GENERAL> >(gx, gy, s, a, tm, a.pdl != 0);
+    }
+}
+#else
+int launch_colt8(int, int, int, int, rt_stream, const ColArgs&, const void*) { return -1; }
+#endif
+#endif
+
 // the whole GS loop of a small square field in one cooperative kernel (slmgs_loop.h): 256 .. 1024 points per line.
 // query_blocks_per_sm != 0: return the resident blocks per SM at this geometry instead of launching.
 #if SLMGS_N >= 256 && SLMGS_N <= 1024 && !defined(SLMGS_EMULATE)

@@ -480,6 +480,8 @@ struct ColArgs {
     long long fld_bs;
     const cf* twA;  // twiddle tables for N = H
     const cf* twB;
+    const cf* tw2A;  // twiddle tables for N = H / 2 (ColKernelT8: 8192-point columns as two interleaved 4096-point lines), or nullptr
+    const cf* tw2B;
     float* weights;       // [B][H][W] rolled
     const float* target;  // [B][H][W] rolled (or shared: target_bs == 0)
     float* phase_ff;      // [B][H][W] rolled

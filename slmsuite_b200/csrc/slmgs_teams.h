@@ -210,6 +210,184 @@ template <int N, int VAR, bool DENSE> struct ColKernelT {
 };
 
 // ------------------------------------------------------------------------------------------------------------------
+// 8192-point columns on the team design (dense fields): decimation in time over the row parity.
+//
+// A 2-column tile of 8192 rows is 128 KB -- no room for a staging buffer and two exchange buffers in one SM, which is why
+// the plain 8192 kernels (32 points per thread, one 512-thread block per SM, load -> compute -> store in series) run at a
+// quarter of the HBM rate.  But in the row-pair interleaved field the even and the odd rows of ONE column sit side by side
+// (16 bytes per row pair), so a 1-column tile is 64 KB and is exactly the shape the 4096 team kernel works on: two lines
+// of 4096 points (line p = rows 2 j + p), interleaved element by element.  The team runs Fft<4096> on both lines -- same
+// exchange buffer, same bank-conflict-free layout, same 16 points per thread in 64 registers -- and one radix-2 step
+// between lane pairs (thread (lt, 0) and (lt, 1) are neighbours in a warp: SHFL.BFLY 1) joins them,
+//     X[k]        = E[k] + W_8192^k O[k]          E'[k] =  X[k] + X[k + 4096]
+//     X[k + 4096] = E[k] - W_8192^k O[k]          O'[k] = (X[k] - X[k + 4096]) conj(W_8192^k)
+// with k = lt + 256 m, so W_8192^k = W_8192^lt (one table value per thread for the whole kernel) x W_32^m (a compile-time
+// constant).  Thread (lt, p) then holds the far field at rows k + 4096 p of its column: the constraint and the far-field
+// stores are ColKernel's own functions with the image offsets of those rows.  Tiles move as 16 TMA boxes of
+// {1 column x 2 row parities (16 bytes), 256 row pairs}; the other half of every 32-byte sector belongs to the neighbouring
+// column, which the neighbouring block works on at the same time (L2 serves the second request).
+// MODE: COL_FUSED (forward, constraint, inverse, tile out through the exchange buffer) or COL_FWD (forward + far-field
+// outputs: the pre-pass of the global-dependency weight updates, e.g. per-spot feedback).
+//
+// MEASURED AND LEFT OPT-IN (SLMGS_TEAMS8=1; tools/ab_teams8.py, B200, dense 8192^2): results agree with the plain kernels
+// (1e-6 .. 1e-7 on well-conditioned targets) but it is slower -- GS 1229 -> 1306 us per iteration, WGS-Kim 1365 -> 2090,
+// spot feedback 1574 -> 1511: the 16-byte TMA rows double the number of row requests per tile and every field / image
+// access uses half a sector (the plain kernels with 1-column tiles lose in the same way: fused column kernel 548 -> 783 us).
+// ------------------------------------------------------------------------------------------------------------------
+template <int MODE, int VAR> struct ColKernelT8 {
+    static constexpr int N2 = 8192, N = 4096;
+    typedef ColKernel<N, MODE, VAR, 2, true> Base;
+    typedef typename Base::F F;
+    typedef ColArgs Args;
+    static constexpr int C = 2, E = F::E, NS = F::NS;
+    static constexpr int T = C * F::TPL;
+    static constexpr int TILE_BYTES = N2 * (int)sizeof(cf);
+    static constexpr int NWARP = T / 32;
+    static constexpr int BOX_PAIRS = 256, NBOX = N / BOX_PAIRS;
+    static constexpr int EXCH_BYTES = ((F::PADN * C * (int)sizeof(cf)) + 127) / 128 * 128;
+    static_assert(NS == 3 && E == 16 && F::R0 == 16 && F::last_radix() == 16 && NBOX == NWARP, "Fft<4096>: 16 * 16 * 16");
+    static_assert(EXCH_BYTES >= TILE_BYTES, "the output tile is staged in the exchange buffer");
+    static constexpr int TW_BYTES = (F::TWS_A + F::TWS_B) * (int)sizeof(cf);
+    static size_t smem_bytes() { return (size_t)TILE_BYTES + 2 * (size_t)EXCH_BYTES + TW_BYTES + 64; }
+
+    static SLMGS_DEVICE void team_bar(int team) { asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(T) : "memory"); }
+    static SLMGS_DEVICE cf shfl1(cf x) {
+        return make_float2(__shfl_xor_sync(0xffffffffu, x.x, 1), __shfl_xor_sync(0xffffffffu, x.y, 1));
+    }
+    // box j = row pairs [256 j, 256 j + 256) of column q: 512 consecutive staging elements; issued by lane 0 of warp j
+    static SLMGS_DEVICE void issue_load(const void* tmap, cf* stage, unsigned long long* bar, int q, int by, int tid) {
+        if ((tid & 31) != 0) return;
+        if (tid == 0) mbar_expect_tx(bar, (unsigned)TILE_BYTES);
+        const int j = tid >> 5;
+        tma_load_box2(stage + (size_t)j * BOX_PAIRS * 2, tmap, q * 2, j * BOX_PAIRS, by, bar);
+    }
+    static SLMGS_DEVICE void issue_store(const void* tmap, const cf* exch, int q, int by, int tid) {
+        if ((tid & 31) != 0) return;
+        const int j = tid >> 5;
+        tma_store_box2(tmap, q * 2, j * BOX_PAIRS, by, exch + (size_t)j * BOX_PAIRS * 2);
+        bulk_commit();
+    }
+    // the far-field image block of a column PAIR (tile-major images, 2 columns per tile) into L2
+    static SLMGS_DEVICE void prefetch_images(const Args& a, int q, int by) {
+        if (q & 1) return;  // (the even neighbour fetches the block for both)
+        constexpr unsigned BYTES = (unsigned)(N2 * 2 * sizeof(float));
+        const long long off = (long long)(q >> 1) * N2 * 2;
+        bulk_prefetch_l2(a.weights + (long long)by * a.img_bs + off, BYTES);
+        if (MODE == COL_FWD || VAR == VAR_POW || VAR == VAR_POW_STORED || VAR == VAR_GENERAL)
+            bulk_prefetch_l2(a.target + (long long)by * a.target_bs + off, BYTES);
+        if (VAR == VAR_POW_STORED) bulk_prefetch_l2(a.phase_ff + (long long)by * a.img_bs + off, BYTES);
+    }
+    template <int M> static SLMGS_DEVICE void join(cf* v, cf wb, bool odd) {
+        if constexpr (M < 16) {
+            const cf t = ctwiddle_const<1, 32, M>(cmul(v[M], wb));  // W^k O[k] (odd lanes)
+            const cf r = shfl1(odd ? t : v[M]);
+            v[M] = odd ? csub(r, t) : cadd(v[M], r);
+            join<M + 1>(v, wb, odd);
+        }
+    }
+    template <int M> static SLMGS_DEVICE void split(cf* v, cf wb, bool odd) {
+        if constexpr (M < 16) {
+            const cf r = shfl1(v[M]);
+            const cf d = odd ? csub(r, v[M]) : cadd(v[M], r);
+            v[M] = odd ? ctwiddle_const<-1, 32, M>(cmulc(d, wb)) : d;
+            split<M + 1>(v, wb, odd);
+        }
+    }
+
+    static SLMGS_DEVICE void run(const Args& a, const void* tmap, unsigned char* smem_raw) {
+        cf* stage = reinterpret_cast<cf*>(smem_raw);
+        const int team = threadIdx.x / T;
+        cf* exch = reinterpret_cast<cf*>(smem_raw + TILE_BYTES + (size_t)team * EXCH_BYTES);
+        cf* tws = reinterpret_cast<cf*>(smem_raw + TILE_BYTES + 2 * (size_t)EXCH_BYTES);
+        unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + TILE_BYTES + 2 * (size_t)EXCH_BYTES + TW_BYTES);
+        // twiddle rows of the 4096-point lines (a.tw2A / a.tw2B: the tables of N / 2)
+        for (int e = threadIdx.x; e < F::TWS_A + F::TWS_B; e += 2 * T) {
+            if (e < F::TWS_A) tws[e] = __ldg(a.tw2A + (1 << (e / F::M1)) * F::M1 + e % F::M1);
+            else tws[e] = __ldg(a.tw2B + (1 << ((e - F::TWS_A) / F::R2)) * F::R2 + (e - F::TWS_A) % F::R2);
+        }
+        SmemTw twA, twB;
+        twA.p = tws;
+        twB.p = tws + F::TWS_A;
+        ThreadId id;
+        id.tid = threadIdx.x % T;
+        id.nthreads = T;
+        id.by = blockIdx.y;
+        id.gx = a.W;
+        id.it = 0;
+        const int ntiles = a.W;
+        const int n_my = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const bool elected = (id.tid & 31) == 0;
+        const bool odd = (id.tid & 1) != 0;
+        const int lt = id.tid >> 1;
+        // W_8192^lt: row k0 = 1 of the first twiddle table of the 8192-point plan (twA[k0 M1 + j] = W_N^(j k0), lt < M1)
+        const cf wb = __ldg(a.twA + Fft<N2>::M1 + lt);
+        if (threadIdx.x == 0) {
+            mbar_init(full + 0, 1);
+            mbar_init(full + 1, 1);
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // (see ColKernelT::run)
+        __syncthreads();
+        if (team == 0 && n_my > 0) issue_load(tmap, stage, full + 0, blockIdx.x, id.by, id.tid);
+        typename Base::State st;
+        const cf* sp = stage + id.tid;  // staged element (row pair j, parity p) at 2 j + p; this thread: j = lt + 256 m
+        for (int i = team, k = 0; i < n_my; i += 2, ++k) {
+            const int q = (int)blockIdx.x + i * (int)gridDim.x;
+            id.bx = q;
+            typename Base::Loc L;
+            L.C = C;
+            L.col = id.tid & 1;
+            L.lt = lt;
+            L.gc = q;
+            L.s = exch + L.col;
+            L.fbase = 0;
+            {   // image_index(k + 4096 p, q, 8192, 2): rows k + 4096 p of column q in the tile-major images
+                const long long ioff = (long long)(q >> 1) * N2 * 2 + (long long)L.col * N * 2 + (q & 1);
+                L.ibase = (long long)id.by * a.img_bs + ioff;
+                L.tbase = (long long)id.by * a.target_bs + ioff;
+            }
+            mbar_wait(full + team, (unsigned)(k & 1));
+            SLMGS_UNROLL
+            for (int m = 0; m < 16; ++m) st.v[m] = sp[2 * F::TPL * m];
+            F::template fwd_compute_u<0, 0>(st.v);
+            F::template fwd_twiddle_u<0, 0>(st.v, lt, twA, twB);
+            if (MODE == COL_FUSED && elected) bulk_wait_read0();  // this team's previous tile has left the exchange buffer
+            team_bar(team);                                       // ... and every thread of the team has read the staging buffer
+            if (i + 1 < n_my) {
+                issue_load(tmap, stage, full + (team ^ 1), q + (int)gridDim.x, id.by, id.tid);
+                if (id.tid == 32 * (NWARP - 1) + 1) prefetch_images(a, q + (int)gridDim.x, id.by);
+            }
+            F::template store_scrambled_u<0, 0>(st.v, lt, L.s, C);
+            team_bar(team);
+            NoSync sy;
+            F::template fwd_stage_sy<1>(st.v, lt, twA, twB, L.s, C, sy);
+            team_bar(team);
+            if constexpr (MODE == COL_FUSED) Base::prefetch_images_head(a, L);
+            F::template fwd_stage_sy<2>(st.v, lt, twA, twB, L.s, C, sy);
+            join<0>(st.v, wb, odd);
+            if constexpr (MODE == COL_FWD) {
+                Base::store_farfield(st, a, id, L);
+            } else {
+                Base::template constrain<false>(st, a, id, L);
+                split<0>(st.v, wb, odd);
+                F::template inv_stage_sy<2>(st.v, lt, twA, twB, L.s, C, sy);
+                team_bar(team);
+                F::template inv_stage_sy<1>(st.v, lt, twA, twB, L.s, C, sy);
+                team_bar(team);
+                F::template inv_stage_sy<0>(st.v, lt, twA, twB, L.s, C, sy);
+                team_bar(team);  // the exchange buffer has been read: it now takes the output tile
+                cf* op = exch + id.tid;
+                SLMGS_UNROLL
+                for (int m = 0; m < 16; ++m) op[2 * F::TPL * m] = st.v[m];
+                fence_async_smem();
+                team_bar(team);
+                issue_store(tmap, exch, q, id.by, id.tid);
+            }
+        }
+        if (MODE == COL_FUSED && elected) bulk_wait0();
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
 // The fused row kernel with the same structure.  A team owns one ROW PAIR: in the row-pair interleaved field that is
 // one contiguous block of 2 W complex values, so tile in / tile out are single 1-D bulk copies (cp.async.bulk), and a
 // thread's element k of line l sits at staging index 2 k + l = tid + 2 TPL m: lane-linear, conflict free.

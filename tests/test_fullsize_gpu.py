@@ -471,3 +471,38 @@ def test_team_kernels_amp_array_and_propagation_kernel(cuda, slm, monkeypatch):
         ref = gs_oracle.OracleHologram(target, amp=amp, phase=phase, slm_shape=slm, propagation_kernel=prop)
         ref.optimize(**kw)
     assert rel_rmse(out[0][1], ref.amp_ff) <= 1e-5
+
+
+@pytest.mark.parametrize("case", ["gs_dense_target", "kim_spots", "spot_feedback"])
+def test_8192_split_column_team_kernels_vs_plain(cuda, case, monkeypatch):
+    """The opt-in 8192-point team column kernels (csrc/slmgs_teams.h ColKernelT8: a column as two interleaved
+    4096-point lines joined by one radix-2 step between lane pairs, SLMGS_TEAMS8=1) use a different factorisation than
+    the plain 8192 kernels, so they agree to rounding, not bit for bit: fused GS, the in-kernel power-law update across
+    the phase-fixing iteration, and the forward pre-pass of the per-spot feedback."""
+    from slmsuite_b200 import Hologram, SpotHologram
+
+    n = 8192
+    rng = np.random.default_rng(21)
+    phase = rng.uniform(-np.pi, np.pi, (n, n)).astype(np.float32)
+    out = []
+    for teams8 in ("1", "0"):
+        monkeypatch.setenv("SLMGS_TEAMS8", teams8)
+        monkeypatch.setenv("SLMGS_SPARSE", "0")
+        if case == "gs_dense_target":
+            h = Hologram(np.random.default_rng(22).random((n, n), dtype=np.float32), phase=phase, slm_shape=(n, n))
+            h.optimize("GS", maxiter=2, verbose=False)
+        elif case == "kim_spots":
+            h = Hologram(_spots((n, n), 2000, 23), phase=phase, slm_shape=(n, n))
+            h.optimize("WGS-Kim", maxiter=5, verbose=False, fix_phase_iteration=3)
+        else:
+            v = np.random.default_rng(5).uniform(64, n - 64, (2, 2000))
+            h = SpotHologram((n, n), v, basis="knm")
+            h.reset_phase(phase)
+            h.optimize("WGS-Leonardo", maxiter=3, verbose=False, feedback="computational_spot")
+        out.append((h.amp_ff.copy(), np.asarray(h.weights).copy(), h.phase.copy()))
+        del h
+    (amp1, w1, ph1), (amp0, w0, ph0) = out
+    assert rel_rmse(amp1, amp0) <= 1e-5
+    assert rel_rmse(w1, w0) <= 1e-5
+    d = np.angle(np.exp(1j * (ph1.astype(np.float64) - ph0)))
+    assert np.sqrt(np.mean(d * d)) <= 2e-5

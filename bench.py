@@ -457,13 +457,14 @@ def run_b200(args, rank, local_rank, world):
         ph = np.random.default_rng(3000 + rank).uniform(-np.pi, np.pi, SHAPE).astype(np.float32)
         kw = dict(method="WGS-Leonardo", maxiter=100, feedback="computational_spot", verbose=False)
         h.reset_phase(ph)
+        h._check(lib.slmgs_save_phase(h._ctx))
         h.optimize(**kw)
         h._check(lib.slmgs_sync(h._ctx))
         barrier()
         reps = 2
         h._check(lib.slmgs_timer_start(h._ctx))
-        for _ in range(reps):
-            h.reset_phase(ph)
+        for _ in range(reps):  # a device-resident step, as the headline's: restore the initial phase, reset the weights, optimize
+            h._check(lib.slmgs_restore_phase(h._ctx))
             h.reset(reset_phase=False)
             h.optimize(**kw)
         t = C.c_float()
@@ -471,7 +472,7 @@ def run_b200(args, rank, local_rank, world):
         t_ms = max_over_ranks(float(t.value))
         used, n_active, n_tiles = h.sparse_info()
         return {"what": "BASELINE configs[2]: SpotHologram 32x32 spots on 4096x4096, WGS-Leonardo, computational_spot "
-                        "feedback, 100 iterations (timed region includes the 64 MB phase upload of every step)",
+                        "feedback, 100 iterations per step (device-resident step: phase restore + weights reset + optimize)",
                 "value": world * reps * 100 / (t_ms * 1e-3), "unit": "it/s", "ms_per_step": t_ms / reps, "steps": reps,
                 "sparse_far_field": {"used": bool(used), "active_column_tiles": int(n_active), "column_tiles": int(n_tiles)}}
 

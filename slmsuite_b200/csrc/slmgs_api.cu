@@ -947,7 +947,7 @@ static RowArgs row_args(slmgs_ctx* c) {
     a.zero_acc = nullptr;
     a.zero_bs = ACC_N;
     a.pdl = (c->use_pdl && !c->profiling) ? 1 : 0;
-    a.pf_dist = c->prefetch ? c->sms * (c->row_threads <= 512 ? 2 : 1) : 0;
+    a.pf_dist = c->prefetch ? c->sms * (c->row_threads <= 512 && c->irow.E <= 16 ? 2 : 1) : 0;  // (= blocks resident on the GPU)
     a.pairs = c->pairs ? 1 : 0;
     if (c->sparse_now) {
         a.colflag = c->tile_byte;
@@ -991,7 +991,7 @@ static ColArgs col_args(slmgs_ctx* c) {
     a.zero_w = c->zero_w;
     a.zero_factor = 1.0f;
     a.pdl = (c->use_pdl && !c->profiling) ? 1 : 0;
-    a.pf_dist = c->prefetch ? c->sms * (c->col_threads <= 512 ? 2 : 1) : 0;
+    a.pf_dist = c->prefetch ? c->sms * (c->col_threads <= 512 && c->icol.E <= 16 ? 2 : 1) : 0;  // (= blocks resident on the GPU)
     if (c->sparse_now) {
         a.tiles = c->tile_list;
         a.tile_count = c->tile_count;

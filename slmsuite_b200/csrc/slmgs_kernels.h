@@ -426,6 +426,17 @@ template <int N, int MODE, bool STORE = false, bool SPARSE = false, int LI = 1, 
             if (a.zero_acc2 && id.bx == 0 && id.tid == 0) a.zero_acc2[(long long)id.by * a.zero_bs] = 0.0;
             if (a.win_dst && id.bx == 0 && id.tid == 0)
                 a.win_dst[id.by] = (float)(1.0 / sqrt(a.win_src[(long long)id.by * a.zero_bs]));
+            if (MODE != ROW_FIRST && LI == 2 && N >= 8192 && a.pf_dist > 0 && !a.colflag) {
+                // 8192-point rows, row-pair interleaved field: the block's two lines are one contiguous 2 W block; pull the
+                // row pair this SM runs next into L2 (one 512-thread block per SM: nothing else hides the head of a tile;
+                // fused row kernel of configs[4] 426 -> 406 us)
+                const int nsr = (id.bx + a.pf_dist) * 2;
+                if (nsr < a.h) {
+                    const int nfr = (nsr + a.i0 + (a.H >> 1)) & (a.H - 1);
+                    const char* base = reinterpret_cast<const char*>(a.fld + (long long)id.by * a.fld_bs + (long long)(nfr >> 1) * a.W * 2);
+                    for (int i = id.tid; i < (int)(2 * N * sizeof(cf) / 128); i += id.nthreads) prefetch_l2(base + (size_t)i * 128);
+                }
+            }
             if (MODE != ROW_FIRST && LI == 1 && a.pf_dist > 0) {
                 // pull the rows of the tile this SM will run next into L2 while this tile computes
                 const int lines = id.nthreads / F::TPL;
@@ -875,6 +886,8 @@ template <int N, int MODE, int VAR = 0, int CT = 0, bool DENSE = false> struct C
         } else {
             if constexpr (P == 0) {
                 load_rows(st, a, L);
+                // (8192-point columns, row-pair interleaved field: one prefetch.global.L2 per 32-byte sector of the next tile
+                // was measured SLOWER -- fused column kernel 531 -> 562 us -- the head of a tile is not what that kernel waits for)
                 if (a.pf_dist > 0 && a.h == a.H && !a.tiles && !a.pairs) {
                     // dense field: pull the rows of the tile group this SM will run next into L2 (a 128-byte line
                     // holds 16 columns = several tiles, so one tile of each line-sharing group issues the prefetch)

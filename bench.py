@@ -216,6 +216,9 @@ def run_b200(args, rank, local_rank, world):
 
     lib = _lib.use_library(_lib.DEFAULT_LIBRARY)
     fp = C.POINTER(C.c_float)
+    # one process per GPU: host threads and pinned buffers on the cores next to this rank's GPU (matters for the
+    # end-to-end copies on a two-socket box; SLMGS_BENCH_NUMA=0 switches it off for A/B runs)
+    numa_cpus = _lib.bind_host_to_device(local_rank) if os.environ.get("SLMGS_BENCH_NUMA", "1") != "0" else None
     torch.cuda.set_device(local_rank)
     # one process per GPU (torchrun sets RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*): the package's own communicator --
     # TCP rendezvous + NCCL loaded inside libslmgs.so (slmgs_comm_* / slmgs_allgather_phase); no torch.distributed
@@ -650,7 +653,9 @@ def run_b200(args, rank, local_rank, world):
                    "target": f"dense random: every far-field column tile is processed ({head_info[1]}/{head_info[2]} "
                              f"active, sparse path used: {bool(head_info[0])})",
                    "l2": "working set 201 MB/iteration (field 134 MB + weights 67 MB) > 126 MB L2, no flush needed",
-                   "final_allgather_ms": ag_ms, "geometry": geometry},
+                   "final_allgather_ms": ag_ms, "geometry": geometry,
+                   "host_cores_bound": (f"{len(numa_cpus)} cores next to the GPU (sysfs local_cpulist)" if numa_cpus
+                                        else "not bound")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "it/s", "h2d_bytes_per_step": int(8 * P), "d2h_bytes_per_step": int(4 * P),
                 "ms_per_step": e2e_ms / args.steps,

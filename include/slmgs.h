@@ -88,6 +88,10 @@ SLMGS_API int slmgs_sync(slmgs_ctx* ctx);
 /* device pointer of the [batch][h][w] float32 phase buffer (for an NCCL all-gather of final phases) */
 SLMGS_API void* slmgs_phase_device_ptr(slmgs_ctx* ctx);
 SLMGS_API void* slmgs_stream(slmgs_ctx* ctx);
+/* PCI bus id ("0000:1b:00.0", NUL terminated) of CUDA device `device`: lets a multi-GPU host place its threads and pinned
+ * buffers on the NUMA node next to the GPU (slmsuite_b200/_lib.py bind_host_to_device).  Host utility of the one-process-
+ * per-GPU deployment; the reference is single GPU and has no counterpart. */
+SLMGS_API int slmgs_device_pci_bus_id(int device, char* out, int len);
 
 /* ---- state upload / download ------------------------------------------------------------ */
 SLMGS_API int slmgs_set_phase(slmgs_ctx*, const float* phase);            /* reset_phase, :570-601; [B][h][w] */

@@ -62,6 +62,7 @@ SIGNATURES = {
     "slmgs_sync": (C.c_int, [_ctx]),
     "slmgs_phase_device_ptr": (C.c_void_p, [_ctx]),
     "slmgs_stream": (C.c_void_p, [_ctx]),
+    "slmgs_device_pci_bus_id": (C.c_int, [C.c_int, C.c_char_p, C.c_int]),
     "slmgs_set_phase": (C.c_int, [_ctx, _fp]),
     "slmgs_get_phase": (C.c_int, [_ctx, _fp]),
     "slmgs_set_amp_scalar": (C.c_int, [_ctx, C.c_float]),
@@ -174,6 +175,38 @@ def lib():
         except OSError as exc:
             raise RuntimeError("slmsuite_b200: cannot load {}: {}".format(DEFAULT_LIBRARY, exc)) from exc
     return _lib
+
+
+def _parse_cpulist(text):
+    """'0-3,8,10-11' -> [0, 1, 2, 3, 8, 10, 11] (the format of sysfs cpulist files)."""
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_device(device):
+    """One process per GPU: run this process (and allocate what it pins from now on) on the host cores next to CUDA
+    device ``device`` -- the ``local_cpulist`` of the GPU's PCI function in sysfs.  On a two-socket 8-GPU box the
+    host <-> device copies of the end-to-end path otherwise cross the socket interconnect for half of the ranks.
+    Returns the core list, or None when the topology is not visible (nothing is changed then)."""
+    buf = C.create_string_buffer(32)
+    try:
+        if lib().slmgs_device_pci_bus_id(int(device), buf, 32) != 0 or not buf.value:
+            return None
+        with open("/sys/bus/pci/devices/{}/local_cpulist".format(buf.value.decode().lower())) as fh:
+            cpus = _parse_cpulist(fh.read())
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except (OSError, ValueError, AttributeError):
+        return None
 
 
 class SlmgsError(RuntimeError):

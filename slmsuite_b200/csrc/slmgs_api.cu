@@ -682,6 +682,19 @@ extern "C" int slmgs_destroy(slmgs_ctx* c) {
     return SLMGS_OK;
 }
 
+extern "C" int slmgs_device_pci_bus_id(int device, char* out, int len) {
+    if (!out || len < 13) return SLMGS_ERR_INVALID;
+    out[0] = 0;
+#ifndef SLMGS_EMULATE
+    if (cudaDeviceGetPCIBusId(out, len, device) != cudaSuccess) {
+        cudaGetLastError();
+        out[0] = 0;
+        return SLMGS_ERR_CUDA;
+    }
+#endif
+    return SLMGS_OK;
+}
+
 extern "C" int slmgs_sync(slmgs_ctx* c) {
     CHECK_CTX(c);
     RT(c, rt_sync(c->stream));

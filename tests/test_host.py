@@ -281,3 +281,17 @@ def test_spot_window_edges_and_feedback_names(emu):
         h2.optimize("WGS-Leonardo", maxiter=3, verbose=False, feedback="computational_spot")
     with pytest.raises(NotImplementedError, match="camera"):
         h.optimize("WGS-Leonardo", maxiter=2, verbose=False, feedback="experimental_spot")
+
+
+def test_parse_cpulist_and_bind_is_harmless_without_a_gpu():
+    """bind_host_to_device: sysfs cpulist parsing; without a visible GPU topology nothing is changed."""
+    import os
+
+    from slmsuite_b200 import _lib
+
+    assert _lib._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert _lib._parse_cpulist("") == []
+    before = os.sched_getaffinity(0)
+    out = _lib.bind_host_to_device(0)
+    assert out is None or set(out) <= before
+    os.sched_setaffinity(0, before)

@@ -70,8 +70,12 @@ template <int OP> struct ElemKernel {
         const long long stride = (long long)id.gx * id.nthreads;
         for (long long i = (long long)id.bx * id.nthreads + id.tid; i < a.n; i += stride) {
             if (OP == EW_ROLL_F32 || OP == EW_ROLL_C64) {
-                const int y = (int)(i / a.W), x = (int)(i % a.W);
-                const long long j = image_index((y + (a.H >> 1)) % a.H, (x + (a.W >> 1)) % a.W, a.H, a.C);
+                // H, W and C are powers of two: shifts and masks instead of 64-bit divisions (which made this kernel
+                // instruction bound: 124 instructions per element, 113 us for a 4096^2 image)
+                const int lw = ilog2(a.W), lc = ilog2(a.C);
+                const int y = (int)(i >> lw), x = (int)(i & (a.W - 1));
+                const int ry = (y + (a.H >> 1)) & (a.H - 1), rx = (x + (a.W >> 1)) & (a.W - 1);
+                const long long j = (((long long)(rx >> lc) * a.H + ry) << lc) + (rx & (a.C - 1));  // == image_index(ry, rx, H, C)
                 if (OP == EW_ROLL_F32) {
                     if (a.unroll) dstf[i] = srcf[j];
                     else dstf[j] = srcf[i];
